@@ -1,0 +1,109 @@
+"""ctypes binding of libclstm.so (the C ABI in include/clstm.h).
+
+There is deliberately no fallback: if the shared library is missing or no sm_100 device is
+present, every product entry point raises.  ``oracle/`` is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclstm.so")
+
+CLSTM_F16 = 0
+CLSTM_BF16 = 1
+DTYPES = {"fp16": CLSTM_F16, "f16": CLSTM_F16, "float16": CLSTM_F16, "bf16": CLSTM_BF16, "bfloat16": CLSTM_BF16}
+
+
+class ClstmError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libclstm error {code}: {message}")
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    """Mirror of clstm_config_t (include/clstm.h)."""
+
+    _fields_ = [
+        ("batch", c_int32),
+        ("height", c_int32),
+        ("width", c_int32),
+        ("in_channels", c_int32),
+        ("hidden", c_int32),
+        ("out_channels", c_int32),
+        ("n_layers", c_int32),
+        ("kernel_h", c_int32),
+        ("kernel_w", c_int32),
+        ("t_in", c_int32),
+        ("t_out", c_int32),
+        ("dtype", c_int32),
+        ("training", c_int32),
+        ("grad_scale", c_float),
+    ]
+
+
+_PROTOTYPES = {
+    "clstm_last_error": (c_char_p, []),
+    "clstm_abi_version": (c_int, []),
+    "clstm_device_check": (c_int, [c_int]),
+    "clstm_plan_create": (c_int, [POINTER(Config), POINTER(c_void_p)]),
+    "clstm_plan_destroy": (c_int, [c_void_p]),
+    "clstm_plan_workspace_bytes": (c_size_t, [c_void_p]),
+    "clstm_plan_bind": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "clstm_plan_set_weights": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p]),
+    "clstm_rollout_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "clstm_rollout_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "clstm_plan_read_state": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "clstm_cell_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "clstm_cell_plan_destroy": (c_int, [c_void_p]),
+    "clstm_cell_plan_workspace_bytes": (c_size_t, [c_void_p]),
+    "clstm_cell_plan_bind": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "clstm_cell_forward": (c_int, [c_void_p] + [c_void_p] * 7 + [c_void_p]),
+    "clstm_cell_backward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_void_p]),
+    "clstm_launch_count": (c_uint64, []),
+    "clstm_selftest_shifted_desc": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libclstm.so (built in-tree by ``__graft_entry__.build()``); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ClstmError(
+                -100,
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU / eager fallback for this path.",
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise ClstmError(rc, lib().clstm_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a torch tensor (or NULL for None)."""
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

@@ -1,0 +1,1103 @@
+// libclstm.so — host side of the C ABI declared in include/clstm.h.
+//
+// Plans own nothing but descriptors: the caller binds one device workspace, the plan carves it
+// into the HBM-resident tensors of the rollout (DESIGN.md "Data layout in HBM"), encodes the TMA
+// tensor maps once, and every entry point only enqueues kernels on the caller's stream.
+//
+// Reference lines each sequence follows are cited next to it (paths relative to the reference
+// repository root, openclimatefix/satflow v0.3.36).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/clstm.h"
+#include "convgemm.cuh"
+#include "pointwise.cuh"
+#include "selftest.cuh"
+#include "wgrad.cuh"
+
+using namespace clstm;
+
+namespace {
+
+thread_local char g_err[1024] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return fail(CLSTM_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define RC_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+inline int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(CLSTM_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------- device / driver
+struct DeviceInfo {
+  int ordinal = -1;
+  int sms = 0;
+  int smem_optin = 0;
+};
+
+int get_device(DeviceInfo* d) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(CLSTM_ENODEV, "device %d (%s) has compute capability %d.%d; this library is sm_100a only", dev,
+                prop.name, prop.major, prop.minor);
+  d->ordinal = dev;
+  d->sms = prop.multiProcessorCount;
+  d->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return 0;
+}
+
+// NHWC activation tensor [N][H][W][C] of 16-bit elements; box = 64 channels x boxW x boxH x 1 image,
+// 128-byte swizzle, out-of-bounds (including negative coordinates) reads as zero == conv padding.
+int make_map_act(CUtensorMap* m, int dtype, const void* ptr, int C, int W, int H, long long N, int boxW, int boxH) {
+  EncodeTiledFn enc;
+  RC_TRY(get_encode(&enc));
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, dtype == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%lld box %dx%d) -> %d", C, W, H, N, boxW,
+                boxH, (int)r);
+  return 0;
+}
+
+// Packed weight matrix [rows][K] (K-major); box = 64 k x boxRows rows.
+int make_map_w(CUtensorMap* m, int dtype, const void* ptr, int K, int rows, int boxRows) {
+  EncodeTiledFn enc;
+  RC_TRY(get_encode(&enc));
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)boxRows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, dtype == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(weights K=%d rows=%d box %d) -> %d", K, rows, boxRows, (int)r);
+  return 0;
+}
+
+// --------------------------------------------------------------------------- geometry
+struct Geo {
+  int B, H, W;
+  int BW, BH, tiles_w, tiles_h;      // 128-pixel tiles (pixel-major GEMMs)
+  int BW2, BH2, tiles_w2, tiles_h2;  // 64-pixel tiles (wgrad K steps)
+  size_t npix() const { return static_cast<size_t>(B) * H * W; }
+};
+
+Geo make_geo(int B, int H, int W) {
+  Geo g;
+  g.B = B, g.H = H, g.W = W;
+  int bw = 8;
+  while (bw < W && bw < 128) bw <<= 1;
+  g.BW = bw, g.BH = 128 / bw;
+  g.tiles_w = (W + g.BW - 1) / g.BW, g.tiles_h = (H + g.BH - 1) / g.BH;
+  g.BW2 = bw > 64 ? 64 : bw, g.BH2 = 64 / g.BW2;
+  g.tiles_w2 = (W + g.BW2 - 1) / g.BW2, g.tiles_h2 = (H + g.BH2 - 1) / g.BH2;
+  return g;
+}
+
+int pad_hidden(int hid) {
+  if (hid <= 64) return 64;
+  if (hid <= 128) return 128;
+  if (hid <= 256) return 256;
+  if (hid <= 512) return 512;
+  return -1;
+}
+
+const int kPackBlocks = 148 * 8;
+const int kGateGradBlocks = 148 * 4;
+const int kHeadBiasChunks = 148;
+
+// Everything a cell step needs besides the cell itself.
+struct Ctx {
+  DeviceInfo dev;
+  Geo geo;
+  int dtype = CLSTM_F16;
+  int HP = 0;
+  int training = 0;
+  float grad_scale = 0.f;
+  void* dz = nullptr;      // E [npix][4HP]
+  float* scale = nullptr;  // device {S, 1/S}
+  unsigned int* amax = nullptr;
+  CUtensorMap m_dz128, m_dz64;
+};
+
+struct CellState {
+  CellGeom g;
+  int T = 0;       // steps this cell runs per rollout
+  int Kf = 0;      // forward K
+  int Kd = 0;      // dgrad K
+  int rows_d = 0;  // dgrad output columns
+  int with_x = 0;
+  int n_tile_d = 0;
+  int slots_h = 0, slots_c = 0;
+  int wg_total = 0, wg_group = 0, wg_splits = 0;
+  bool bwd_started = false;
+  // packed parameters
+  void* wp = nullptr;
+  float* bias_p = nullptr;
+  void* wd = nullptr;
+  // state stacks
+  void* h = nullptr;      // E [slots_h][npix][HP]
+  float* c = nullptr;     // fp32 [slots_c][npix][HP]
+  void* gates = nullptr;  // E [T][npix][4HP] (training)
+  // backward scratch
+  float* dh_own = nullptr;  // fp32 [npix][HP]
+  float* dxb = nullptr;     // fp32 [npix][CIP]
+  float* dc = nullptr;      // fp32 [npix][HP]
+  float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
+  float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
+  CUtensorMap m_h128, m_h64, m_wp, m_wd;
+
+  size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
+};
+
+// Where a cell's input comes from at one step.
+struct InputRef {
+  const CUtensorMap* map128 = nullptr;
+  const CUtensorMap* map64 = nullptr;
+  int b_off = 0;  // image offset (slot * B)
+};
+
+struct Carver {
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t bytes) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+void wgrad_shape(const DeviceInfo& dev, int total_blocks, int n_blocks, long long p_tiles, int* group_size,
+                 int* splits) {
+  int groups = (total_blocks + kWgMaxGroupBlocks - 1) / kWgMaxGroupBlocks;
+  int gs = (total_blocks + groups - 1) / groups;
+  groups = (total_blocks + gs - 1) / gs;
+  int sms = dev.sms > 0 ? dev.sms : 148;
+  long long sp = sms / (groups * n_blocks);
+  if (sp > p_tiles) sp = p_tiles;
+  if (sp < 1) sp = 1;
+  *group_size = gs;
+  *splits = static_cast<int>(sp);
+}
+
+// Fills the derived fields of a cell.  in_col: the input is an im2col'd tensor (rollout encoder_1).
+void init_cell(CellState* cs, const Ctx& ctx, int cin, int hid, int kh, int kw, int in_col, int with_x, int T) {
+  CellGeom& g = cs->g;
+  g.cin = cin, g.hid = hid, g.HP = ctx.HP, g.kh = kh, g.kw = kw, g.in_col = in_col;
+  g.CIP = round_up(cin, 64);
+  g.KIN = in_col ? round_up(kh * kw * cin, 64) : kh * kw * g.CIP;
+  cs->T = T;
+  cs->Kf = g.KIN + kh * kw * g.HP;
+  cs->Kd = kh * kw * 4 * g.HP;
+  cs->with_x = with_x;
+  cs->rows_d = (with_x ? g.CIP : 0) + g.HP;
+  int nt = 256;
+  while (cs->rows_d % nt) nt -= 64;
+  cs->n_tile_d = nt;
+  cs->wg_total = cs->Kf / 64;
+  const long long p_tiles = static_cast<long long>(ctx.geo.B) * ctx.geo.tiles_w2 * ctx.geo.tiles_h2;
+  wgrad_shape(ctx.dev, cs->wg_total, 4 * g.HP / 128, p_tiles, &cs->wg_group, &cs->wg_splits);
+}
+
+void carve_cell(Carver& cv, CellState& cs, const Ctx& ctx) {
+  const size_t npix = ctx.geo.npix();
+  const int HP = ctx.HP;
+  cs.wp = cv.take<void>(static_cast<size_t>(4 * HP) * cs.Kf * 2);
+  cs.bias_p = cv.take<float>(static_cast<size_t>(4 * HP) * 4);
+  cs.h = cv.take<void>(static_cast<size_t>(cs.slots_h) * npix * HP * 2);
+  cs.c = cv.take<float>(static_cast<size_t>(cs.slots_c) * npix * HP * 4);
+  if (ctx.training) {
+    cs.wd = cv.take<void>(static_cast<size_t>(cs.rows_d) * cs.Kd * 2);
+    cs.gates = cv.take<void>(static_cast<size_t>(cs.T) * npix * 4 * HP * 2);
+    cs.dh_own = cv.take<float>(npix * HP * 4);
+    cs.dxb = cs.with_x ? cv.take<float>(npix * cs.g.CIP * 4) : nullptr;
+    cs.dc = cv.take<float>(npix * HP * 4);
+    cs.wpart = cv.take<float>(static_cast<size_t>(cs.wg_splits) * 4 * HP * cs.Kf * 4);
+    cs.bpart = cv.take<float>(static_cast<size_t>(kGateGradBlocks) * 4 * HP * 4);
+  }
+}
+
+int map_cell(CellState& cs, const Ctx& ctx) {
+  const Geo& g = ctx.geo;
+  const long long imgs = static_cast<long long>(cs.slots_h) * g.B;
+  RC_TRY(make_map_act(&cs.m_h128, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
+  RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
+  RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256));
+  if (ctx.training) RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
+  return 0;
+}
+
+// --------------------------------------------------------------------------- launch helpers
+template <typename E, int EPI>
+int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                    ConvGemmParams p, const Geo& g, long long images, cudaStream_t st) {
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  const int stage_bytes = kABytes + p.n_tile * 128;
+  const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles));
+  int stages = (dev.smem_optin - fixed) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return fail(CLSTM_EINVAL, "convgemm: not enough shared memory for n_tile=%d", p.n_tile);
+  p.stages = stages;
+  const size_t smem = convgemm_smem_bytes(stages, p.n_tile, p.n_tiles);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(convgemm_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dev.smem_optin));
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.n_tiles;
+  const int grid = total < dev.sms ? total : dev.sms;
+  convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, p);
+  return after_launch("convgemm_kernel");
+}
+
+template <typename E>
+int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
+                 WgradParams p, const Geo& g, long long images, cudaStream_t st) {
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW2, p.BH = g.BH2, p.tiles_w = g.tiles_w2, p.tiles_h = g.tiles_h2;
+  p.num_p_tiles = static_cast<int>(images) * g.tiles_w2 * g.tiles_h2;
+  const int stage_bytes = (2 + p.group_size) * kWgTileP * 128;
+  int stages = (dev.smem_optin - static_cast<int>(wgrad_smem_bytes(0, 0))) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return fail(CLSTM_EINVAL, "wgrad: not enough shared memory");
+  p.stages = stages;
+  const size_t smem = wgrad_smem_bytes(stages, p.group_size);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  const int groups = (p.total_blocks + p.group_size - 1) / p.group_size;
+  const int grid = groups * p.n_blocks * p.splits;
+  wgrad_kernel<E><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p);
+  return after_launch("wgrad_kernel");
+}
+
+// --------------------------------------------------------------------------- cell building blocks
+// Repack one cell's reference-layout parameters (layers/ConvLSTM.py:34-40 weight/bias).
+template <typename E>
+int pack_cell(const Ctx& ctx, CellState& cs, const float* w, const float* bias, cudaStream_t st) {
+  pack_cell_weights_fwd_kernel<E><<<kPackBlocks, 256, 0, st>>>(w, bias, static_cast<E*>(cs.wp), cs.bias_p, cs.g);
+  RC_TRY(after_launch("pack_cell_weights_fwd_kernel"));
+  if (ctx.training) {
+    pack_cell_weights_dgrad_kernel<E><<<kPackBlocks, 256, 0, st>>>(w, static_cast<E*>(cs.wd), cs.g, cs.with_x);
+    RC_TRY(after_launch("pack_cell_weights_dgrad_kernel"));
+  }
+  return 0;
+}
+
+// One fused cell step (layers/ConvLSTM.py:42-57): reads the input tensor and h slot `sp`, c_prev;
+// writes h slot `sn`, c_next (and the gates when training).
+template <typename E>
+int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int sn, const float* c_prev,
+                      float* c_next, void* gates, cudaStream_t st) {
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const CellGeom& g = cs.g;
+  p.n_tiles = ctx.HP / 64;
+  p.n_tile = 256;
+  p.nseg = 2;
+  if (g.in_col)
+    p.seg[0] = ConvSeg{g.KIN / 64, 1, 1, in.b_off};
+  else
+    p.seg[0] = ConvSeg{g.CIP / 64, g.kh, g.kw, in.b_off};
+  p.seg[1] = ConvSeg{ctx.HP / 64, g.kh, g.kw, sp * ctx.geo.B};
+  p.bias = cs.bias_p;
+  p.c_prev = c_prev;
+  p.c_next = c_next;
+  p.h_next = static_cast<E*>(cs.h) + static_cast<size_t>(sn) * cs.h_slot_elems(ctx.geo);
+  p.gates = gates;
+  p.ldc = ctx.HP;
+  return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
+}
+
+// Backward of one cell step: fused gate gradient -> dgrad (dx | dh_prev) -> wgrad accumulation.
+// dh sources (fp32 NHWC, scaled by S) may be null.  c_prev may be null (zeros).
+template <typename E>
+int cell_backward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, const void* gates,
+                       const float* c_prev, const float* c_next, const float* dh0, const float* dh1,
+                       const float* dh2, cudaStream_t st) {
+  const CellGeom& g = cs.g;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int first = cs.bwd_started ? 0 : 1;
+  cs.bwd_started = true;
+  // (1) pointwise gate gradient (backward of layers/ConvLSTM.py:48-55)
+  gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 33 * sizeof(float), st>>>(
+      static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dz), cs.bpart, !first,
+      npix, ctx.HP);
+  RC_TRY(after_launch("gate_grad_kernel"));
+  // (2) dgrad: d[x | h_prev] = conv_transpose(dz, W)  (backward of :45-47)
+  {
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_tile = cs.n_tile_d;
+    p.n_tiles = cs.rows_d / cs.n_tile_d;
+    p.nseg = 1;
+    p.seg[0] = ConvSeg{4 * ctx.HP / 64, g.kh, g.kw, 0};
+    p.out0 = cs.dxb;
+    p.out1 = cs.dh_own;
+    p.split_col = cs.with_x ? g.CIP : 0;
+    p.ld0 = g.CIP;
+    p.ld1 = ctx.HP;
+    p.out_scale = 1.f;
+    RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, geo, geo.B, st)));
+  }
+  // (3) wgrad: dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
+  {
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_blocks = 4 * ctx.HP / 128;
+    p.group_size = cs.wg_group;
+    p.total_blocks = cs.wg_total;
+    if (g.in_col)
+      p.seg[0] = WgradSeg{g.KIN / 64, g.KIN / 64, 1, 0, 0, in.b_off};
+    else
+      p.seg[0] = WgradSeg{g.kh * g.kw * (g.CIP / 64), g.CIP / 64, g.kw, g.kh / 2, g.kw / 2, in.b_off};
+    p.seg[1] = WgradSeg{g.kh * g.kw * (ctx.HP / 64), ctx.HP / 64, g.kw, g.kh / 2, g.kw / 2, sp * geo.B};
+    p.a_b_off = 0;
+    p.splits = cs.wg_splits;
+    p.partial = cs.wpart;
+    p.accumulate = !first;
+    RC_TRY((launch_wgrad<E>(ctx.dev, ctx.m_dz64, *in.map64, cs.m_h64, p, geo, geo.B, st)));
+  }
+  return 0;
+}
+
+// Reduce the split partial sums into reference-layout gradients (unscaled by 1/S).
+int cell_finalize(const Ctx& ctx, CellState& cs, float* dw, float* db, int accumulate, cudaStream_t st) {
+  const CellGeom& g = cs.g;
+  if (dw) {
+    cell_wgrad_finalize_kernel<<<kPackBlocks, 256, 0, st>>>(cs.wpart, dw, g, cs.wg_splits, ctx.scale + 1,
+                                                            accumulate);
+    RC_TRY(after_launch("cell_wgrad_finalize_kernel"));
+  }
+  if (db) {
+    cell_bias_finalize_kernel<<<(4 * g.hid + 255) / 256, 256, 0, st>>>(cs.bpart, db, kGateGradBlocks, g.hid,
+                                                                       ctx.HP, ctx.scale + 1, accumulate);
+    RC_TRY(after_launch("cell_bias_finalize_kernel"));
+  }
+  return 0;
+}
+
+int validate_common(int batch, int height, int width, int in_channels, int hidden, int kh, int kw, int dtype) {
+  if (batch < 1 || height < 1 || width < 1 || in_channels < 1 || hidden < 1)
+    return fail(CLSTM_EINVAL, "batch/height/width/channels/hidden must be positive");
+  if (kh < 1 || kw < 1 || (kh % 2) == 0 || (kw % 2) == 0 || kh > 7 || kw > 7)
+    return fail(CLSTM_EINVAL,
+                "kernel size (%d,%d) unsupported: odd sizes up to 7 only (the reference itself breaks on even "
+                "kernels, layers/ConvLSTM.py:32-54)",
+                kh, kw);
+  if (pad_hidden(hidden) < 0) return fail(CLSTM_EINVAL, "hidden_dim %d > 512 unsupported", hidden);
+  if (dtype != CLSTM_F16 && dtype != CLSTM_BF16) return fail(CLSTM_EINVAL, "dtype must be CLSTM_F16 or CLSTM_BF16");
+  if (static_cast<long long>(batch) * height * width > (1ll << 30))
+    return fail(CLSTM_EINVAL, "batch*height*width too large");
+  return 0;
+}
+
+#define DISPATCH_E(dtype, call)          \
+  ((dtype) == CLSTM_F16 ? call(__half) : call(__nv_bfloat16))
+
+}  // namespace
+
+// ============================================================================ rollout plan
+struct clstm_plan {
+  clstm_config_t cfg;
+  Ctx ctx;
+  int L = 0, ncell = 0, KX = 0, KG = 0, NT = 0;
+  size_t ws_bytes = 0;
+  bool bound = false, weights_set = false, forward_done = false;
+  std::vector<CellState> cells;
+  void* xcol = nullptr;       // E [T_in*B][H][W][KX]
+  void* G = nullptr;          // E [npix][KG]
+  float* dstack = nullptr;    // fp32 [npix][HP]
+  void* wh = nullptr;         // E [NT][9HP]
+  float* bias_h = nullptr;    // fp32 [NT]
+  void* whd = nullptr;        // E [n_tile_hd rows = HP][KG]
+  float* hpart = nullptr;     // fp32 [splits][128*(KG/128)][HP]
+  float* hbpart = nullptr;    // fp32 [C_out][kHeadBiasChunks]
+  int head_splits = 0, head_group = 0, n_tile_hd = 0;
+  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd;
+};
+
+namespace {
+
+void carve_plan(clstm_plan* p, uint8_t* base) {
+  Carver cv;
+  cv.base = base;
+  const clstm_config_t& c = p->cfg;
+  Ctx& ctx = p->ctx;
+  const size_t npix = ctx.geo.npix();
+  const int HP = ctx.HP;
+  ctx.scale = cv.take<float>(64);
+  ctx.amax = reinterpret_cast<unsigned int*>(cv.take<float>(64));
+  p->xcol = cv.take<void>(static_cast<size_t>(c.t_in) * npix * p->KX * 2);
+  for (int k = 0; k < p->ncell; ++k) carve_cell(cv, p->cells[k], ctx);
+  p->wh = cv.take<void>(static_cast<size_t>(p->NT) * 9 * HP * 2);
+  p->bias_h = cv.take<float>(static_cast<size_t>(p->NT) * 4);
+  if (c.training) {
+    ctx.dz = cv.take<void>(npix * 4 * HP * 2);
+    p->G = cv.take<void>(npix * p->KG * 2);
+    p->dstack = cv.take<float>(npix * HP * 4);
+    p->whd = cv.take<void>(static_cast<size_t>(HP) * p->KG * 2);
+    p->hpart = cv.take<float>(static_cast<size_t>(p->head_splits) * p->KG * HP * 4);
+    p->hbpart = cv.take<float>(static_cast<size_t>(c.out_channels) * kHeadBiasChunks * 4);
+  }
+  p->ws_bytes = align_up(cv.off, 1024);
+}
+
+// slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
+inline int hslot(const CellState& cs, int s) { return s % cs.slots_h; }
+inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
+
+// Input of cell k at its step t (conv_lstm.py:176-196).
+InputRef plan_input(clstm_plan* p, int k, int t) {
+  InputRef in;
+  const int B = p->cfg.batch;
+  const int L = p->L;
+  if (k == 0) {
+    in.map128 = &p->m_xcol128, in.map64 = &p->m_xcol64, in.b_off = t * B;  // x[:, t]  (:177)
+  } else if (k == L) {
+    // decoder_1 input: encoder_vector (:185, :189) = last encoder h at t == 0, else last decoder h (:195)
+    const CellState& src = (t == 0) ? p->cells[L - 1] : p->cells[p->ncell - 1];
+    const int s = (t == 0) ? hslot(src, p->cfg.t_in) : hslot(src, t);
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.b_off = s * B;
+  } else {
+    const CellState& src = p->cells[k - 1];  // the layer below, already stepped to t + 1 (:180, :192)
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.b_off = hslot(src, t + 1) * B;
+  }
+  return in;
+}
+
+template <typename E>
+int plan_set_weights(clstm_plan* p, const float* const* params, cudaStream_t st) {
+  for (int k = 0; k < p->ncell; ++k) RC_TRY(pack_cell<E>(p->ctx, p->cells[k], params[2 * k], params[2 * k + 1], st));
+  const float* wh = params[2 * p->ncell];
+  const float* bh = params[2 * p->ncell + 1];
+  pack_head_weights_fwd_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, bh, static_cast<E*>(p->wh), p->bias_h,
+                                                               p->cfg.out_channels, p->cfg.hidden, p->ctx.HP, p->NT);
+  RC_TRY(after_launch("pack_head_weights_fwd_kernel"));
+  if (p->cfg.training) {
+    pack_head_weights_dgrad_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, static_cast<E*>(p->whd), p->cfg.out_channels,
+                                                                   p->cfg.hidden, p->ctx.HP, p->KG);
+    RC_TRY(after_launch("pack_head_weights_dgrad_kernel"));
+  }
+  return 0;
+}
+
+template <typename E>
+int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
+  const clstm_config_t& c = p->cfg;
+  const Ctx& ctx = p->ctx;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  const int L = p->L;
+  // x (B,T,C,H,W) -> im2col'd 16-bit tensor, once for all T_in steps
+  pack_xcol_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels,
+                                                   c.height, c.width, c.kernel_h, c.kernel_w, p->KX);
+  RC_TRY(after_launch("pack_xcol_kernel"));
+  if (!c.training) {
+    // ring-buffered states: slot 0 must read as the zero initial state (layers/ConvLSTM.py:59-64)
+    for (int k = 0; k < p->ncell; ++k) CU_TRY(cudaMemsetAsync(p->cells[k].h, 0, npix * HP * 2, st));
+  }
+  auto step = [&](int k, int t) -> int {
+    CellState& cs = p->cells[k];
+    const InputRef in = plan_input(p, k, t);
+    const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
+    float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
+    void* gates = c.training ? static_cast<void*>(static_cast<E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP)
+                             : nullptr;
+    return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st);
+  };
+  for (int t = 0; t < c.t_in; ++t)  // conv_lstm.py:176-183
+    for (int l = 0; l < L; ++l) RC_TRY(step(l, t));
+  for (int t = 0; t < c.t_out; ++t)  // conv_lstm.py:188-196
+    for (int l = 0; l < L; ++l) RC_TRY(step(L + l, t));
+  // head: Conv3d(1,3,3) + Sigmoid over the stacked last-decoder h (conv_lstm.py:198-201)
+  {
+    ConvGemmParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.n_tile = p->NT;
+    hp.n_tiles = 1;
+    hp.nseg = 1;
+    hp.seg[0] = ConvSeg{HP / 64, 3, 3, 1 * c.batch};  // slots 1..T_out
+    hp.bias = p->bias_h;
+    hp.y = y;
+    hp.c_out = c.out_channels;
+    hp.t_out = c.t_out;
+    hp.b_img = c.batch;
+    const CellState& last = p->cells[p->ncell - 1];
+    RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo,
+                                         static_cast<long long>(c.t_out) * c.batch, st)));
+  }
+  p->forward_done = true;
+  return 0;
+}
+
+template <typename E>
+int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* grads, int accumulate,
+                  cudaStream_t st) {
+  const clstm_config_t& c = p->cfg;
+  Ctx& ctx = p->ctx;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  const int L = p->L, ncell = p->ncell;
+  const size_t ny = static_cast<size_t>(c.batch) * c.out_channels * c.t_out * c.height * c.width;
+
+  // loss scale for the 16-bit gradient operands (device side, no sync)
+  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 4, st));
+  if (!(c.grad_scale > 0.f)) {
+    head_grad_amax_kernel<<<kPackBlocks, 256, 0, st>>>(dy, y, ny, ctx.amax);
+    RC_TRY(after_launch("head_grad_amax_kernel"));
+  }
+  choose_scale_kernel<<<1, 1, 0, st>>>(ctx.amax, ctx.scale, ctx.dtype == CLSTM_F16 ? 1024.f : 1.f, c.grad_scale);
+  RC_TRY(after_launch("choose_scale_kernel"));
+
+  for (int k = 0; k < ncell; ++k) {
+    p->cells[k].bwd_started = false;
+    CU_TRY(cudaMemsetAsync(p->cells[k].dc, 0, npix * HP * 4, st));
+  }
+  // head bias gradient: sum of dlogit (unscaled, straight from dy and y)
+  {
+    dim3 grid(kHeadBiasChunks, c.out_channels);
+    head_bias_partial_kernel<<<grid, 256, 0, st>>>(dy, y, p->hbpart, c.batch, c.out_channels, c.t_out, c.height,
+                                                   c.width);
+    RC_TRY(after_launch("head_bias_partial_kernel"));
+    float* db = grads[2 * ncell + 1];
+    if (db) {
+      reduce_rows_kernel<<<(c.out_channels + 63) / 64, 64, 0, st>>>(p->hbpart, db, c.out_channels, kHeadBiasChunks, 1,
+                                                                    kHeadBiasChunks, 1.f, accumulate);
+      RC_TRY(after_launch("reduce_rows_kernel"));
+    }
+  }
+
+  auto back = [&](int k, int t, const float* e1, const float* e2) -> int {
+    CellState& cs = p->cells[k];
+    const InputRef in = plan_input(p, k, t);
+    const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP;
+    const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
+    const float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
+    const float* own = (t == cs.T - 1) ? nullptr : cs.dh_own;
+    return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st);
+  };
+
+  CellState& last = p->cells[ncell - 1];
+  const float* dfeed = nullptr;  // grad wrt the decoder input of step t + 1
+  for (int t = c.t_out - 1; t >= 0; --t) {
+    // head backward for this output frame: dlogit "col" tensor -> dgrad into dstack, wgrad accumulation
+    head_grad_col_kernel<E><<<kPackBlocks, 256, 0, st>>>(dy, y, static_cast<E*>(p->G), c.batch, c.out_channels,
+                                                         c.t_out, c.height, c.width, p->KG, t, 1, ctx.scale);
+    RC_TRY(after_launch("head_grad_col_kernel"));
+    {
+      ConvGemmParams hp;
+      memset(&hp, 0, sizeof(hp));
+      hp.n_tile = p->n_tile_hd;
+      hp.n_tiles = HP / p->n_tile_hd;
+      hp.nseg = 1;
+      hp.seg[0] = ConvSeg{p->KG / 64, 1, 1, 0};
+      hp.out0 = p->dstack, hp.out1 = p->dstack;
+      hp.split_col = HP, hp.ld0 = HP, hp.ld1 = HP;
+      hp.out_scale = 1.f;
+      RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st)));
+    }
+    {
+      WgradParams wp;
+      memset(&wp, 0, sizeof(wp));
+      wp.n_blocks = p->KG / 128;
+      wp.group_size = p->head_group;
+      wp.total_blocks = HP / 64;
+      wp.seg[0] = WgradSeg{HP / 64, HP / 64, 1, 0, 0, hslot(last, t + 1) * c.batch};
+      wp.seg[1] = WgradSeg{0, 1, 1, 0, 0, 0};
+      wp.splits = p->head_splits;
+      wp.partial = p->hpart;
+      wp.accumulate = (t != c.t_out - 1);
+      RC_TRY((launch_wgrad<E>(ctx.dev, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st)));
+    }
+    RC_TRY(back(ncell - 1, t, p->dstack, dfeed));
+    for (int k = ncell - 2; k >= L; --k) RC_TRY(back(k, t, p->cells[k + 1].dxb, nullptr));
+    dfeed = p->cells[L].dxb;
+  }
+  for (int t = c.t_in - 1; t >= 0; --t) {
+    RC_TRY(back(L - 1, t, (t == c.t_in - 1) ? dfeed : nullptr, nullptr));
+    for (int k = L - 2; k >= 0; --k) RC_TRY(back(k, t, p->cells[k + 1].dxb, nullptr));
+  }
+  for (int k = 0; k < ncell; ++k) RC_TRY(cell_finalize(ctx, p->cells[k], grads[2 * k], grads[2 * k + 1], accumulate, st));
+  if (grads[2 * ncell]) {
+    const int total = c.out_channels * c.hidden * 9;
+    head_wgrad_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(p->hpart, grads[2 * ncell], c.out_channels,
+                                                                    c.hidden, HP, p->KG, p->head_splits,
+                                                                    ctx.scale + 1, accumulate);
+    RC_TRY(after_launch("head_wgrad_finalize_kernel"));
+  }
+  return 0;
+}
+
+template <typename E>
+int plan_read_state(clstm_plan* p, int cell, int step, float* h_out, float* c_out, cudaStream_t st) {
+  const clstm_config_t& c = p->cfg;
+  CellState& cs = p->cells[cell];
+  const size_t npix = p->ctx.geo.npix();
+  const int HP = p->ctx.HP;
+  if (h_out) {
+    const E* src = static_cast<const E*>(cs.h) + static_cast<size_t>(hslot(cs, step)) * npix * HP;
+    unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(src, h_out, c.batch, c.hidden, c.height, c.width, HP, nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  if (c_out) {
+    if (step == 0) {
+      CU_TRY(cudaMemsetAsync(c_out, 0, static_cast<size_t>(c.batch) * c.hidden * c.height * c.width * 4, st));
+    } else {
+      const float* src = cs.c + static_cast<size_t>(cslot(cs, step)) * npix * HP;
+      unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(src, c_out, c.batch, c.hidden, c.height, c.width, HP,
+                                                             nullptr, 0);
+      RC_TRY(after_launch("unpack_nchw_kernel"));
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================ single-cell plan
+struct clstm_cell_plan {
+  Ctx ctx;
+  CellState cs;
+  int cin = 0, hid = 0;
+  size_t ws_bytes = 0;
+  bool bound = false, forward_done = false;
+  void* xin = nullptr;  // E [npix][CIP]
+  CUtensorMap m_x128, m_x64;
+};
+
+namespace {
+
+void carve_cell_plan(clstm_cell_plan* p, uint8_t* base) {
+  Carver cv;
+  cv.base = base;
+  Ctx& ctx = p->ctx;
+  const size_t npix = ctx.geo.npix();
+  ctx.scale = cv.take<float>(64);
+  ctx.amax = reinterpret_cast<unsigned int*>(cv.take<float>(64));
+  p->xin = cv.take<void>(npix * p->cs.g.CIP * 2);
+  carve_cell(cv, p->cs, ctx);
+  ctx.dz = cv.take<void>(npix * 4 * ctx.HP * 2);
+  p->ws_bytes = align_up(cv.off, 1024);
+}
+
+template <typename E>
+int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, const float* c_cur,
+                     const float* weight, const float* bias, float* h_next, float* c_next, cudaStream_t st) {
+  Ctx& ctx = p->ctx;
+  CellState& cs = p->cs;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  const size_t plane = static_cast<size_t>(geo.H) * geo.W;
+  RC_TRY(pack_cell<E>(ctx, cs, weight, bias, st));
+  pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xin), geo.B, p->cin, geo.H, geo.W, cs.g.CIP,
+                                                   p->cin * plane);
+  RC_TRY(after_launch("pack_nhwc_kernel"));
+  pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(h_cur, static_cast<E*>(cs.h), geo.B, p->hid, geo.H, geo.W, HP,
+                                                   p->hid * plane);
+  RC_TRY(after_launch("pack_nhwc_kernel"));
+  pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(c_cur, cs.c, geo.B, p->hid, geo.H, geo.W, HP, nullptr);
+  RC_TRY(after_launch("pack_nhwc_f32_kernel"));
+  InputRef in;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
+  RC_TRY(cell_forward_step<E>(ctx, cs, in, 0, 1, cs.c, cs.c + npix * HP, cs.gates, st));
+  if (h_next) {
+    unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(static_cast<const E*>(cs.h) + npix * HP, h_next, geo.B, p->hid,
+                                                       geo.H, geo.W, HP, nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  if (c_next) {
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.c + npix * HP, c_next, geo.B, p->hid, geo.H, geo.W, HP,
+                                                           nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  p->forward_done = true;
+  return 0;
+}
+
+template <typename E>
+int cellplan_backward(clstm_cell_plan* p, const float* dh_next, const float* dc_next, const float* weight,
+                      float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, cudaStream_t st) {
+  Ctx& ctx = p->ctx;
+  CellState& cs = p->cs;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  (void)weight;  // the packed copies made by the preceding forward are used
+  // Loss scale for the 16-bit dz operand: S = 2^k with S * max(|dh_next|, |dc_next|) ~ 2^10 (device side).
+  const size_t nstate = static_cast<size_t>(geo.B) * p->hid * geo.H * geo.W;
+  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 4, st));
+  if (dh_next) {
+    abs_amax_kernel<<<kPackBlocks, 256, 0, st>>>(dh_next, nstate, ctx.amax);
+    RC_TRY(after_launch("abs_amax_kernel"));
+  }
+  if (dc_next) {
+    abs_amax_kernel<<<kPackBlocks, 256, 0, st>>>(dc_next, nstate, ctx.amax);
+    RC_TRY(after_launch("abs_amax_kernel"));
+  }
+  choose_scale_kernel<<<1, 1, 0, st>>>(ctx.amax, ctx.scale, ctx.dtype == CLSTM_F16 ? 1024.f : 1.f, 0.f);
+  RC_TRY(after_launch("choose_scale_kernel"));
+  // upstream gradients -> NHWC fp32, scaled (dh into dh_own as source 0, dc into the in-place dc buffer)
+  float* dh_src = nullptr;
+  if (dh_next) {
+    pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(dh_next, cs.dh_own, geo.B, p->hid, geo.H, geo.W, HP, ctx.scale);
+    RC_TRY(after_launch("pack_nhwc_f32_kernel"));
+    dh_src = cs.dh_own;
+  }
+  if (dc_next) {
+    pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(dc_next, cs.dc, geo.B, p->hid, geo.H, geo.W, HP, ctx.scale);
+    RC_TRY(after_launch("pack_nhwc_f32_kernel"));
+  } else {
+    CU_TRY(cudaMemsetAsync(cs.dc, 0, npix * HP * 4, st));
+  }
+  cs.bwd_started = false;
+  InputRef in;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
+  RC_TRY(cell_backward_step<E>(ctx, cs, in, 0, cs.gates, cs.c, cs.c + npix * HP, dh_src, nullptr, nullptr, st));
+  RC_TRY(cell_finalize(ctx, cs, dweight, dbias, 0, st));
+  if (dx) {
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dxb, dx, geo.B, p->cin, geo.H, geo.W, cs.g.CIP,
+                                                           ctx.scale + 1, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  if (dh_cur) {
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dh_own, dh_cur, geo.B, p->hid, geo.H, geo.W, HP, nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  if (dc_cur) {
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dc, dc_cur, geo.B, p->hid, geo.H, geo.W, HP, nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+const char* clstm_last_error(void) { return g_err; }
+int clstm_abi_version(void) { return CLSTM_ABI_VERSION; }
+uint64_t clstm_launch_count(void) { return g_launches.load(); }
+
+int clstm_device_check(int ordinal) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(CLSTM_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  if (ordinal < 0 || ordinal >= n) return fail(CLSTM_ENODEV, "device ordinal %d out of range (%d devices)", ordinal, n);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, ordinal));
+  if (prop.major != 10)
+    return fail(CLSTM_ENODEV, "device %d (%s) is sm_%d%d; libclstm is sm_100a only", ordinal, prop.name, prop.major,
+                prop.minor);
+  return 0;
+}
+
+int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
+  if (!cfg || !out) return fail(CLSTM_EINVAL, "null argument");
+  *out = nullptr;
+  RC_TRY(validate_common(cfg->batch, cfg->height, cfg->width, cfg->in_channels, cfg->hidden, cfg->kernel_h,
+                         cfg->kernel_w, cfg->dtype));
+  if (cfg->out_channels < 1 || cfg->out_channels > 256) return fail(CLSTM_EINVAL, "out_channels must be in [1,256]");
+  if (cfg->n_layers < 1 || cfg->n_layers > 8) return fail(CLSTM_EINVAL, "n_layers must be in [1,8]");
+  if (cfg->t_in < 1) return fail(CLSTM_EINVAL, "t_in must be >= 1");
+  if (cfg->t_out < 1)
+    return fail(CLSTM_EINVAL,
+                "t_out (forecast_steps) must be >= 1: the reference raises on an empty output stack "
+                "(conv_lstm.py:198)");
+  clstm_plan* p = new (std::nothrow) clstm_plan();
+  if (!p) return fail(CLSTM_EINVAL, "out of host memory");
+  p->cfg = *cfg;
+  Ctx& ctx = p->ctx;
+  // Device properties are optional at create time (sizes do not depend on them except the wgrad split,
+  // which falls back to 148 SMs); bind re-checks the device.
+  DeviceInfo dev;
+  if (get_device(&dev) == 0) ctx.dev = dev;
+  ctx.geo = make_geo(cfg->batch, cfg->height, cfg->width);
+  ctx.dtype = cfg->dtype;
+  ctx.HP = pad_hidden(cfg->hidden);
+  ctx.training = cfg->training;
+  ctx.grad_scale = cfg->grad_scale;
+  p->L = cfg->n_layers;
+  p->ncell = 2 * cfg->n_layers;
+  p->KX = round_up(cfg->kernel_h * cfg->kernel_w * cfg->in_channels, 64);
+  p->KG = round_up(9 * cfg->out_channels, 128);
+  p->NT = round_up(cfg->out_channels, 16);
+  p->cells.resize(p->ncell);
+  for (int k = 0; k < p->ncell; ++k) {
+    CellState& cs = p->cells[k];
+    const int T = (k < p->L) ? cfg->t_in : cfg->t_out;
+    init_cell(&cs, ctx, k == 0 ? cfg->in_channels : cfg->hidden, cfg->hidden, cfg->kernel_h, cfg->kernel_w,
+              k == 0 ? 1 : 0, k == 0 ? 0 : 1, T);
+    const bool full = cfg->training || k == p->ncell - 1;  // the head reads every last-decoder h
+    cs.slots_h = full ? T + 1 : 2;
+    cs.slots_c = cfg->training ? T + 1 : 2;
+  }
+  int nt = 256;
+  while (ctx.HP % nt) nt -= 64;
+  p->n_tile_hd = nt;
+  const long long p_tiles = static_cast<long long>(ctx.geo.B) * ctx.geo.tiles_w2 * ctx.geo.tiles_h2;
+  wgrad_shape(ctx.dev, ctx.HP / 64, p->KG / 128, p_tiles, &p->head_group, &p->head_splits);
+  carve_plan(p, nullptr);
+  *out = p;
+  return 0;
+}
+
+int clstm_plan_destroy(clstm_plan_t* plan) {
+  delete plan;
+  return 0;
+}
+
+size_t clstm_plan_workspace_bytes(const clstm_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+
+int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream) {
+  if (!p || !workspace) return fail(CLSTM_EINVAL, "null argument");
+  if (bytes < p->ws_bytes) return fail(CLSTM_EINVAL, "workspace too small: %zu < %zu", bytes, p->ws_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(CLSTM_EINVAL, "workspace must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ctx& ctx = p->ctx;
+  DeviceInfo dev;
+  RC_TRY(get_device(&dev));
+  if (ctx.dev.sms != 0 && ctx.dev.sms != dev.sms)
+    return fail(CLSTM_ESTATE, "plan was created for a device with %d SMs, bound on one with %d", ctx.dev.sms, dev.sms);
+  if (ctx.dev.sms == 0 && dev.sms != 148)
+    return fail(CLSTM_ESTATE, "plan was created without a device and assumed 148 SMs; this device has %d", dev.sms);
+  ctx.dev = dev;
+  carve_plan(p, static_cast<uint8_t*>(workspace));
+  const Geo& g = ctx.geo;
+  const clstm_config_t& c = p->cfg;
+  const size_t npix = g.npix();
+  // zero the initial states (ConvLSTMCell.init_hidden, layers/ConvLSTM.py:59-64) and everything a
+  // tensor map may read before it is written
+  for (int k = 0; k < p->ncell; ++k) {
+    CellState& cs = p->cells[k];
+    CU_TRY(cudaMemsetAsync(cs.h, 0, npix * ctx.HP * 2, st));
+    CU_TRY(cudaMemsetAsync(cs.c, 0, npix * ctx.HP * 4, st));
+    RC_TRY(map_cell(cs, ctx));
+  }
+  const long long ximgs = static_cast<long long>(c.t_in) * c.batch;
+  RC_TRY(make_map_act(&p->m_xcol128, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW, g.BH));
+  RC_TRY(make_map_act(&p->m_xcol64, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW2, g.BH2));
+  RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT));
+  if (c.training) {
+    RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
+    RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
+    RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
+    RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
+    RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
+  }
+  p->bound = true;
+  p->weights_set = false;
+  p->forward_done = false;
+  return 0;
+}
+
+int clstm_plan_set_weights(clstm_plan_t* p, const float* const* params, int n_params, void* stream) {
+  if (!p || !params) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound) return fail(CLSTM_ESTATE, "clstm_plan_set_weights before clstm_plan_bind");
+  if (n_params != 2 * p->ncell + 2)
+    return fail(CLSTM_EINVAL, "expected %d parameter tensors, got %d", 2 * p->ncell + 2, n_params);
+  for (int i = 0; i < n_params; ++i)
+    if (!params[i]) return fail(CLSTM_EINVAL, "parameter %d is null", i);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) plan_set_weights<E>(p, params, st)
+  RC_TRY(DISPATCH_E(p->cfg.dtype, CALL_));
+#undef CALL_
+  p->weights_set = true;
+  return 0;
+}
+
+int clstm_rollout_forward(clstm_plan_t* p, const float* x, float* y, void* stream) {
+  if (!p || !x || !y) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound || !p->weights_set) return fail(CLSTM_ESTATE, "forward before bind / set_weights");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) plan_forward<E>(p, x, y, st)
+  return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_rollout_backward(clstm_plan_t* p, const float* dy, const float* y, float* const* grads, int n_grads,
+                           int accumulate, void* stream) {
+  if (!p || !dy || !y || !grads) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->cfg.training) return fail(CLSTM_ESTATE, "backward on a plan created with training = 0");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "backward before forward");
+  if (n_grads != 2 * p->ncell + 2)
+    return fail(CLSTM_EINVAL, "expected %d gradient tensors, got %d", 2 * p->ncell + 2, n_grads);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) plan_backward<E>(p, dy, y, grads, accumulate, st)
+  return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_plan_read_state(clstm_plan_t* p, int cell, int step, float* h_out, float* c_out, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "read_state before forward");
+  if (cell < 0 || cell >= p->ncell) return fail(CLSTM_EINVAL, "cell index %d out of range", cell);
+  const CellState& cs = p->cells[cell];
+  if (step < 0 || step > cs.T) return fail(CLSTM_EINVAL, "step %d out of range [0,%d]", step, cs.T);
+  if (h_out && cs.slots_h < cs.T + 1 && step < cs.T - 1)
+    return fail(CLSTM_ESTATE, "inference plans keep only the last two h steps of cell %d", cell);
+  if (c_out && cs.slots_c < cs.T + 1 && step < cs.T - 1 && step != 0)
+    return fail(CLSTM_ESTATE, "inference plans keep only the last two c steps of cell %d", cell);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) plan_read_state<E>(p, cell, step, h_out, c_out, st)
+  return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+}
+
+// ---------------------------------------------------------------------------- single cell
+int clstm_cell_plan_create(int batch, int height, int width, int in_channels, int hidden, int kernel_h, int kernel_w,
+                           int dtype, clstm_cell_plan_t** out) {
+  if (!out) return fail(CLSTM_EINVAL, "null argument");
+  *out = nullptr;
+  RC_TRY(validate_common(batch, height, width, in_channels, hidden, kernel_h, kernel_w, dtype));
+  clstm_cell_plan* p = new (std::nothrow) clstm_cell_plan();
+  if (!p) return fail(CLSTM_EINVAL, "out of host memory");
+  Ctx& ctx = p->ctx;
+  DeviceInfo dev;
+  if (get_device(&dev) == 0) ctx.dev = dev;
+  ctx.geo = make_geo(batch, height, width);
+  ctx.dtype = dtype;
+  ctx.HP = pad_hidden(hidden);
+  ctx.training = 1;
+  ctx.grad_scale = 0.f;
+  p->cin = in_channels, p->hid = hidden;
+  init_cell(&p->cs, ctx, in_channels, hidden, kernel_h, kernel_w, 0, 1, 1);
+  p->cs.slots_h = 2, p->cs.slots_c = 2;
+  carve_cell_plan(p, nullptr);
+  *out = p;
+  return 0;
+}
+
+int clstm_cell_plan_destroy(clstm_cell_plan_t* plan) {
+  delete plan;
+  return 0;
+}
+
+size_t clstm_cell_plan_workspace_bytes(const clstm_cell_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+
+int clstm_cell_plan_bind(clstm_cell_plan_t* p, void* workspace, size_t bytes, void* stream) {
+  if (!p || !workspace) return fail(CLSTM_EINVAL, "null argument");
+  if (bytes < p->ws_bytes) return fail(CLSTM_EINVAL, "workspace too small: %zu < %zu", bytes, p->ws_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(CLSTM_EINVAL, "workspace must be 1024-byte aligned");
+  (void)stream;
+  Ctx& ctx = p->ctx;
+  DeviceInfo dev;
+  RC_TRY(get_device(&dev));
+  if (ctx.dev.sms != 0 && ctx.dev.sms != dev.sms) return fail(CLSTM_ESTATE, "plan created for a different device");
+  if (ctx.dev.sms == 0 && dev.sms != 148) return fail(CLSTM_ESTATE, "plan created without a device assumed 148 SMs");
+  ctx.dev = dev;
+  carve_cell_plan(p, static_cast<uint8_t*>(workspace));
+  const Geo& g = ctx.geo;
+  RC_TRY(map_cell(p->cs, ctx));
+  RC_TRY(make_map_act(&p->m_x128, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
+  RC_TRY(make_map_act(&p->m_x64, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, g.BW2, g.BH2));
+  RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
+  RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW2, g.BH2));
+  p->bound = true;
+  p->forward_done = false;
+  return 0;
+}
+
+int clstm_cell_forward(clstm_cell_plan_t* p, const float* x, const float* h_cur, const float* c_cur,
+                       const float* weight, const float* bias, float* h_next, float* c_next, void* stream) {
+  if (!p || !x || !h_cur || !c_cur || !weight) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound) return fail(CLSTM_ESTATE, "clstm_cell_forward before clstm_cell_plan_bind");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) cellplan_forward<E>(p, x, h_cur, c_cur, weight, bias, h_next, c_next, st)
+  return DISPATCH_E(p->ctx.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_cell_backward(clstm_cell_plan_t* p, const float* dh_next, const float* dc_next, const float* weight,
+                        float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "clstm_cell_backward before clstm_cell_forward");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) cellplan_backward<E>(p, dh_next, dc_next, weight, dx, dh_cur, dc_cur, dweight, dbias, st)
+  return DISPATCH_E(p->ctx.dtype, CALL_);
+#undef CALL_
+}
+
+// ---------------------------------------------------------------------------- bring-up experiments
+int clstm_selftest_shifted_desc(float* out_max_abs_err, int n_variants, int n_shifts, void* stream) {
+  if (!out_max_abs_err || n_variants < 1 || n_shifts < 1) return fail(CLSTM_EINVAL, "bad argument");
+  DeviceInfo dev;
+  RC_TRY(get_device(&dev));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return run_shifted_desc_selftest(out_max_abs_err, n_variants, n_shifts, st, &g_launches) == 0
+             ? 0
+             : fail(CLSTM_ECUDA, "shifted-descriptor self test failed to launch: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// Pixel-major implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, n] = sum over K-segments s, taps (dy,dx) of s, channels c of s:
+//                     A_s[pixel + (dy - kh/2, dx - kw/2), c] * Wp[n, k(s,dy,dx,c)]
+//
+// A_s are NHWC activations (fp16/bf16, channel count a multiple of 64) reached through 4-D TMA
+// tensor maps (C, W, H, B): a tap is a coordinate shift, padding is TMA out-of-bounds zero fill,
+// so no im2col buffer and no concat([x,h]) is ever materialised (the reference does both:
+// layers/ConvLSTM.py:45-47).  Wp is the packed weight matrix [N][K] (K-major).  Accumulators live
+// in TMEM (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
+//
+// One kernel serves every pixel-major GEMM of the path through its epilogue:
+//   EPI_LSTM  : fused gates -> c' = f*c + i*g, h' = o*tanh(c')   (layers/ConvLSTM.py:48-55)
+//   EPI_STORE : plain fp32 store of up to two column ranges       (dgrad: dx | dh_prev)
+//   EPI_HEAD  : bias + sigmoid, written as (B, C_out, T, H, W)    (conv_lstm.py:198-201)
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 = idle, warps 4..11 = epilogue (two warps per TMEM lane quadrant, splitting columns).
+#pragma once
+#include "ptx.cuh"
+
+namespace clstm {
+
+enum { EPI_LSTM = 0, EPI_STORE = 1, EPI_HEAD = 2 };
+
+constexpr int kTileM = 128;        // pixels per tile == UMMA M
+constexpr int kBlockK = 64;        // channels per k-block (128 B of fp16/bf16 == one swizzle row)
+constexpr int kABytes = kTileM * 128;
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 384;
+constexpr int kTmemCols = 512;
+
+struct ConvSeg {
+  int chunks;  // 64-channel chunks of this segment's activation tensor
+  int kh, kw;  // taps; (1,1) means "direct" (no shift)
+  int b_off;   // image offset into the segment's tensor map (selects a time slot of a [T*B] stack)
+};
+
+struct ConvGemmParams {
+  // geometry of the activation tensors (all segments share it)
+  int B, H, W;
+  int BW, BH;  // pixel tile, BW * BH == 128
+  int tiles_w, tiles_h;
+  int num_m_tiles;
+  int n_tiles;  // N tiles of n_tile columns each
+  int n_tile;   // UMMA N: multiple of 16, <= 256
+  int nseg;
+  ConvSeg seg[2];
+  int stages;
+  // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
+  const float* bias;  // [n_tiles * n_tile] in packed row order (all epilogues)
+  const float* c_prev;  // fp32 [pixel][ldc] or nullptr (== zeros)
+  float* c_next;        // fp32 [pixel][ldc]
+  void* h_next;         // E    [pixel][ldc]
+  void* gates;          // E    [pixel][4*ldc] ([i|f|o|g] blocks of ldc) or nullptr
+  int ldc;              // padded hidden channels (multiple of 64)
+  // ---- EPI_STORE
+  float* out0;
+  float* out1;
+  int split_col;  // columns [0,split) -> out0, [split, N) -> out1
+  int ld0, ld1;
+  float out_scale;
+  // ---- EPI_HEAD (n_tile == C_out rounded up to 16)
+  float* y;  // (Bimg, C_out, T, H, W); the maps' batch index is t * Bimg + b
+  int c_out, t_out, b_img;
+};
+
+template <typename E, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABytes + p.n_tile * 128;
+  uint8_t* tail = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // n_tiles * n_tile floats
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.n_tiles;
+  int kblocks = 0;
+  for (int s = 0; s < p.nseg; ++s) kblocks += p.seg[s].chunks * p.seg[s].kh * p.seg[s].kw;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.nseg > 1) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (p.bias != nullptr) {
+    for (int i = threadIdx.x; i < p.n_tiles * p.n_tile; i += blockDim.x) bias_s[i] = p.bias[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int b = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH;
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
+          const ConvSeg sg = p.seg[s];
+          for (int dy = 0; dy < sg.kh; ++dy)
+            for (int dx = 0; dx < sg.kw; ++dx)
+              for (int ch = 0; ch < sg.chunks; ++ch, ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_dst = smem + stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
+                            h0 + dy - sg.kh / 2, b + sg.b_off);
+                tma_load_2d(a_dst + kABytes, &tmB, &full_bar[stage], kb * kBlockK, nt * p.n_tile);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(Elem<E>::kFmt, kTileM, p.n_tile, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per K=16 step inside the 128-B swizzle row (start-address field is in 16-B units)
+            umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;   // column half handled by this warp
+    const int r = q * 32 + lane;        // tile row == pixel within tile
+    const int hl = r / p.BW, wl = r % p.BW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int b = mt / (p.tiles_w * p.tiles_h);
+      const int hy = th * p.BH + hl, wx = tw * p.BW + wl;
+      const bool valid = (hy < p.H) && (wx < p.W);
+      const size_t pix = (static_cast<size_t>(b) * p.H + hy) * p.W + wx;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+
+      if constexpr (EPI == EPI_LSTM) {
+        // N tile = [i(64) | f(64) | o(64) | g(64)] for hidden channels nt*64 .. nt*64+63
+        const float* bs = bias_s + nt * 256;
+#pragma unroll 1
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const int j0 = half * 32 + g2 * 16;
+          uint32_t vi[16], vf[16], vo[16], vg[16];
+          tmem_ld16(taddr + 0 + j0, vi);
+          tmem_ld16(taddr + 64 + j0, vf);
+          tmem_ld16(taddr + 128 + j0, vo);
+          tmem_ld16(taddr + 192 + j0, vg);
+          tmem_ld_wait();
+          if (valid) {
+            const size_t off = pix * p.ldc + nt * 64 + j0;
+            float cp[16];
+            if (p.c_prev != nullptr) {
+              const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float4 t = __ldg(src + e);
+                cp[4 * e + 0] = t.x, cp[4 * e + 1] = t.y, cp[4 * e + 2] = t.z, cp[4 * e + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) cp[e] = 0.f;
+            }
+            float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
+              gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
+              go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
+              gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+              cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+              hn[e] = go[e] * fast_tanh(cn[e]);
+            }
+            float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              cdst[e] = make_float4(cn[4 * e], cn[4 * e + 1], cn[4 * e + 2], cn[4 * e + 3]);
+            uint4* hdst = reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + off);
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              hdst[e] = make_uint4(Elem<E>::pack2(hn[8 * e + 0], hn[8 * e + 1]), Elem<E>::pack2(hn[8 * e + 2], hn[8 * e + 3]),
+                                   Elem<E>::pack2(hn[8 * e + 4], hn[8 * e + 5]), Elem<E>::pack2(hn[8 * e + 6], hn[8 * e + 7]));
+            if (p.gates != nullptr) {
+              E* gbase = reinterpret_cast<E*>(p.gates) + pix * (4 * static_cast<size_t>(p.ldc)) + nt * 64 + j0;
+              const float* gsrc[4] = {gi, gf, go, gg};
+#pragma unroll
+              for (int gt = 0; gt < 4; ++gt) {
+                uint4* gd = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(gt) * p.ldc);
+                const float* gv = gsrc[gt];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                  gd[e] = make_uint4(Elem<E>::pack2(gv[8 * e + 0], gv[8 * e + 1]), Elem<E>::pack2(gv[8 * e + 2], gv[8 * e + 3]),
+                                     Elem<E>::pack2(gv[8 * e + 4], gv[8 * e + 5]), Elem<E>::pack2(gv[8 * e + 6], gv[8 * e + 7]));
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_STORE) {
+        const int groups = p.n_tile / 16;
+#pragma unroll 1
+        for (int g = half; g < groups; g += 2) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int col = nt * p.n_tile + g * 16;
+            float* dst = (col < p.split_col) ? (p.out0 + pix * p.ld0 + col)
+                                             : (p.out1 + pix * p.ld1 + (col - p.split_col));
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              d4[e] = make_float4(__uint_as_float(v[4 * e]) * p.out_scale, __uint_as_float(v[4 * e + 1]) * p.out_scale,
+                                  __uint_as_float(v[4 * e + 2]) * p.out_scale, __uint_as_float(v[4 * e + 3]) * p.out_scale);
+          }
+        }
+      } else {  // EPI_HEAD
+        const int groups = p.n_tile / 16;
+        const int t = b / p.b_img, bi = b % p.b_img;
+        const size_t plane = static_cast<size_t>(p.H) * p.W;
+#pragma unroll 1
+        for (int g = half; g < groups; g += 2) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            float* ybase = p.y + ((static_cast<size_t>(bi) * p.c_out) * p.t_out + t) * plane +
+                           static_cast<size_t>(hy) * p.W + wx;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int co = nt * p.n_tile + g * 16 + e;
+              if (co < p.c_out)
+                ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(__uint_as_float(v[e]) + bias_s[co]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+inline size_t convgemm_smem_bytes(int stages, int n_tile, int n_tiles) {
+  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + (2 * kMaxStages + 4) * 8 + 16 +
+         static_cast<size_t>(n_tiles) * n_tile * 4 + 64;
+}
+
+}  // namespace clstm

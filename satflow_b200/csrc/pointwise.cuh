@@ -1,0 +1,536 @@
+// HBM-bound helper kernels of the ConvLSTM path: layout packing, weight repacking, the fused
+// gate-gradient pointwise backward, the head's loss-gradient "col" tensor, split reductions.
+// All are plain coalesced/vectorised SIMT kernels; grids are multiples of the SM count.
+#pragma once
+#include "ptx.cuh"
+
+namespace clstm {
+
+// ------------------------------------------------------------------------------------------
+// x (B,T,C,H,W) fp32  ->  xcol[t][b][h][w][KX]  (im2col of the 12-channel input, k = tap*C + c).
+// The encoder-1 input never changes during the recurrence, so its taps are gathered once per
+// forward; inside the cell kernel the x part is then a plain ("direct") K segment.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void pack_xcol_kernel(const float* __restrict__ x, E* __restrict__ xcol, int B, int T, int C, int H,
+                                 int W, int kh, int kw, int KX) {
+  const int chunks = KX / 8;
+  const size_t total = static_cast<size_t>(T) * B * H * W * chunks;
+  const int kreal = kh * kw * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ck = static_cast<int>(i % chunks);
+    size_t pix = i / chunks;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    pix /= H;
+    const int b = static_cast<int>(pix % B);
+    const int t = static_cast<int>(pix / B);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = ck * 8 + e;
+      float val = 0.f;
+      if (k < kreal) {
+        const int tap = k / C, c = k % C;
+        const int hy = h + tap / kw - kh / 2, wx = w + tap % kw - kw / 2;
+        if (hy >= 0 && hy < H && wx >= 0 && wx < W)
+          val = __ldg(x + (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W + wx);
+      }
+      v[e] = val;
+    }
+    uint4 o = make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]), Elem<E>::pack2(v[4], v[5]),
+                         Elem<E>::pack2(v[6], v[7]));
+    reinterpret_cast<uint4*>(xcol)[i] = o;
+  }
+}
+
+// NCHW fp32 (optionally a (B,T,C,H,W) time slice) -> NHWC E with channel padding (zeros).
+template <typename E>
+__global__ void pack_nhwc_kernel(const float* __restrict__ src, E* __restrict__ dst, int B, int C, int H, int W,
+                                 int CP, size_t src_batch_stride) {
+  const int chunks = CP / 8;
+  const size_t total = static_cast<size_t>(B) * H * W * chunks;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ck = static_cast<int>(i % chunks);
+    size_t pix = i / chunks;
+    const size_t hw = pix % (static_cast<size_t>(H) * W);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(H) * W));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ck * 8 + e;
+      v[e] = (c < C) ? __ldg(src + b * src_batch_stride + static_cast<size_t>(c) * H * W + hw) : 0.f;
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]),
+                                                  Elem<E>::pack2(v[4], v[5]), Elem<E>::pack2(v[6], v[7]));
+  }
+}
+
+// NCHW fp32 -> NHWC fp32 with channel padding.
+__global__ void pack_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H,
+                                     int W, int CP, const float* __restrict__ scale_ptr) {
+  const float scale = scale_ptr ? *scale_ptr : 1.f;
+  const size_t total = static_cast<size_t>(B) * H * W * CP;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CP);
+    const size_t pix = i / CP;
+    const size_t hw = pix % (static_cast<size_t>(H) * W);
+    const size_t b = pix / (static_cast<size_t>(H) * W);
+    dst[i] = (c < C) ? scale * __ldg(src + (b * C + c) * H * W + hw) : 0.f;
+  }
+}
+
+// NHWC (E or fp32, channel stride CP) -> NCHW fp32 (C real channels).  scale applied.
+template <typename S>
+__global__ void unpack_nchw_kernel(const S* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
+                                   int CP, const float* __restrict__ scale_ptr, int accumulate) {
+  const float scale = scale_ptr ? *scale_ptr : 1.f;
+  const size_t total = static_cast<size_t>(B) * C * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t hw = i % (static_cast<size_t>(H) * W);
+    const size_t bc = i / (static_cast<size_t>(H) * W);
+    const int c = static_cast<int>(bc % C);
+    const size_t b = bc / C;
+    float v;
+    if constexpr (sizeof(S) == 4)
+      v = src[(b * H * W + hw) * CP + c];
+    else
+      v = Elem<S>::to_float(src[(b * H * W + hw) * CP + c]);
+    v *= scale;
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight repacking (reference layout fp32 -> packed E).  See DESIGN.md "Packed weights".
+// ------------------------------------------------------------------------------------------
+struct CellGeom {
+  int cin;     // real input channels of the cell
+  int hid;     // real hidden channels
+  int HP;      // hidden channels padded to a multiple of 64
+  int kh, kw;
+  int in_col;  // 1: input segment is the im2col'd x (k = tap*cin + c, KIN = round_up(kh*kw*cin, 64))
+               // 0: input segment is a conv over a CIP-channel NHWC tensor (k = tap*CIP + c, KIN = kh*kw*CIP)
+  int CIP;     // input channels padded to a multiple of 64 (in_col == 0)
+  int KIN;     // K extent of the input segment
+};
+
+// forward: Wp[row = nt*256 + gate*64 + jj][k], bias_p[row]
+template <typename E>
+__global__ void pack_cell_weights_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                             E* __restrict__ wp, float* __restrict__ bias_p, CellGeom g) {
+  const int K = g.KIN + g.kh * g.kw * g.HP;
+  const int rows = 4 * g.HP;
+  const int ctot = g.cin + g.hid;
+  const size_t total = static_cast<size_t>(rows) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int row = static_cast<int>(i / K);
+    const int nt = row / 256, gate = (row % 256) / 64, jj = row % 64;
+    const int j = nt * 64 + jj;
+    float val = 0.f;
+    if (j < g.hid) {
+      const int n_ref = gate * g.hid + j;
+      int c_full = -1, tap = 0;
+      if (k < g.KIN) {
+        if (g.in_col) {
+          if (k < g.kh * g.kw * g.cin) tap = k / g.cin, c_full = k % g.cin;
+        } else {
+          tap = k / g.CIP;
+          const int c = k % g.CIP;
+          if (c < g.cin) c_full = c;
+        }
+      } else {
+        const int kk = k - g.KIN;
+        tap = kk / g.HP;
+        const int c = kk % g.HP;
+        if (c < g.hid) c_full = g.cin + c;
+      }
+      if (c_full >= 0) val = w[(static_cast<size_t>(n_ref) * ctot + c_full) * (g.kh * g.kw) + tap];
+      if (k == 0) bias_p[row] = bias ? bias[n_ref] : 0.f;
+    } else if (k == 0) {
+      bias_p[row] = 0.f;
+    }
+    wp[i] = Elem<E>::from_float(val);
+  }
+}
+
+// dgrad: Wd[row][k = tap'*(4HP) + gate*HP + j] = W[gate*hid + j][c_full(row)][flipped tap']
+//   rows: with_x ? [x part: CIP rows | h part: HP rows] : [h part: HP rows]
+template <typename E>
+__global__ void pack_cell_weights_dgrad_kernel(const float* __restrict__ w, E* __restrict__ wd, CellGeom g,
+                                               int with_x) {
+  const int taps = g.kh * g.kw;
+  const int K = taps * 4 * g.HP;
+  const int xrows = with_x ? g.CIP : 0;
+  const int rows = xrows + g.HP;
+  const int ctot = g.cin + g.hid;
+  const size_t total = static_cast<size_t>(rows) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int row = static_cast<int>(i / K);
+    const int tapf = k / (4 * g.HP);
+    const int n = k % (4 * g.HP);
+    const int gate = n / g.HP, j = n % g.HP;
+    int c_full = -1;
+    if (row < xrows) {
+      if (row < g.cin) c_full = row;
+    } else {
+      const int c = row - xrows;
+      if (c < g.hid) c_full = g.cin + c;
+    }
+    float val = 0.f;
+    if (c_full >= 0 && j < g.hid) {
+      const int tap = taps - 1 - tapf;  // (kh-1-dy', kw-1-dx') in row-major tap index
+      val = w[(static_cast<size_t>(gate * g.hid + j) * ctot + c_full) * taps + tap];
+    }
+    wd[i] = Elem<E>::from_float(val);
+  }
+}
+
+// head forward: Wh[row = co (padded to NT)][k = tap*HP + c] = Whead[co][c][0][tap]; bias padded
+template <typename E>
+__global__ void pack_head_weights_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                             E* __restrict__ wp, float* __restrict__ bias_p, int c_out, int hid,
+                                             int HP, int NT) {
+  const int K = 9 * HP;
+  const size_t total = static_cast<size_t>(NT) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K), row = static_cast<int>(i / K);
+    const int tap = k / HP, c = k % HP;
+    float val = 0.f;
+    if (row < c_out && c < hid) val = w[(static_cast<size_t>(row) * hid + c) * 9 + tap];
+    wp[i] = Elem<E>::from_float(val);
+    if (k == 0) bias_p[row] = (row < c_out) ? bias[row] : 0.f;
+  }
+}
+
+// head dgrad: Whd[row = c (HP rows)][k = tap*c_out + co (padded to KG)] = Whead[co][c][0][tap]
+template <typename E>
+__global__ void pack_head_weights_dgrad_kernel(const float* __restrict__ w, E* __restrict__ wd, int c_out, int hid,
+                                               int HP, int KG) {
+  const size_t total = static_cast<size_t>(HP) * KG;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % KG), c = static_cast<int>(i / KG);
+    float val = 0.f;
+    if (c < hid && k < 9 * c_out) {
+      const int tap = k / c_out, co = k % c_out;
+      val = w[(static_cast<size_t>(co) * hid + c) * 9 + tap];
+    }
+    wd[i] = Elem<E>::from_float(val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused gate-gradient pointwise backward of layers/ConvLSTM.py:49-55 for one cell step.
+//   dh = dh0 + dh1 + dh2 (nullable sources; fp32 NHWC, stride HP)
+//   tc = tanh(c'); do = dh*tc; dct = dc + dh*o*(1-tc^2)
+//   dz = [dct*g*i(1-i), dct*c*f(1-f), do*o(1-o), dct*i*(1-g^2)]  -> E, layout [pixel][4*HP]
+//   dc <- dct*f (in place);  bias-gradient partial sums per block (deterministic two-stage)
+// One thread = one pixel x 8 channels; consecutive threads = consecutive channel groups.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256)
+gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
+                 const float* __restrict__ dh0, const float* __restrict__ dh1, const float* __restrict__ dh2,
+                 float* __restrict__ dc, E* __restrict__ dz, float* __restrict__ bias_partial, int bias_accumulate,
+                 size_t npix, int HP) {
+  extern __shared__ float red[];  // [256][33] padded
+  const int groups = HP / 8;
+  const int grp = threadIdx.x % groups;
+  const int plane = threadIdx.x / groups;
+  const int ppb = blockDim.x / groups;  // pixels per block iteration
+  float bsum[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bsum[a][e] = 0.f;
+
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + plane; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * ppb) {
+    const size_t off = pix * HP + grp * 8;
+    float gv[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const uint4 u = *reinterpret_cast<const uint4*>(gates + pix * 4 * HP + a * HP + grp * 8);
+      const float2 p0 = Elem<E>::unpack2(u.x), p1 = Elem<E>::unpack2(u.y), p2 = Elem<E>::unpack2(u.z),
+                   p3 = Elem<E>::unpack2(u.w);
+      gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+      gv[a][4] = p2.x, gv[a][5] = p2.y, gv[a][6] = p3.x, gv[a][7] = p3.y;
+    }
+    float cp[8], cn[8], dhv[8], dcv[8];
+    auto ld8 = [&](const float* src, float* out) {
+      const float4 a = *reinterpret_cast<const float4*>(src + off);
+      const float4 b = *reinterpret_cast<const float4*>(src + off + 4);
+      out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w, out[4] = b.x, out[5] = b.y, out[6] = b.z, out[7] = b.w;
+    };
+    if (c_prev) {
+      ld8(c_prev, cp);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+    }
+    ld8(c_next, cn);
+    ld8(dc, dcv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dhv[e] = 0.f;
+    float tmp[8];
+    if (dh0) {
+      ld8(dh0, tmp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dhv[e] += tmp[e];
+    }
+    if (dh1) {
+      ld8(dh1, tmp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dhv[e] += tmp[e];
+    }
+    if (dh2) {
+      ld8(dh2, tmp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dhv[e] += tmp[e];
+    }
+    float dzv[4][8], dcn[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float i = gv[0][e], f = gv[1][e], o = gv[2][e], g = gv[3][e];
+      const float tc = fast_tanh(cn[e]);
+      const float d_o = dhv[e] * tc;
+      const float dct = fmaf(dhv[e] * o, 1.f - tc * tc, dcv[e]);
+      dzv[0][e] = dct * g * i * (1.f - i);
+      dzv[1][e] = dct * cp[e] * f * (1.f - f);
+      dzv[2][e] = d_o * o * (1.f - o);
+      dzv[3][e] = dct * i * (1.f - g * g);
+      dcn[e] = dct * f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
+    }
+    *reinterpret_cast<float4*>(dc + off) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+    *reinterpret_cast<float4*>(dc + off + 4) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      *reinterpret_cast<uint4*>(dz + pix * 4 * HP + a * HP + grp * 8) =
+          make_uint4(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]),
+                     Elem<E>::pack2(dzv[a][4], dzv[a][5]), Elem<E>::pack2(dzv[a][6], dzv[a][7]));
+    }
+  }
+  // block reduction of the bias partial sums over the `ppb` pixel lanes (fixed order -> deterministic)
+  float* mine = red + threadIdx.x * 33;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine[a * 8 + e] = bsum[a][e];
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    for (int v = 0; v < 32; ++v) {
+      float s = 0.f;
+      for (int pl = 0; pl < ppb; ++pl) s += red[(pl * groups + threadIdx.x) * 33 + v];
+      const int a = v / 8, e = v % 8;
+      float* dst = bias_partial + static_cast<size_t>(blockIdx.x) * 4 * HP + a * HP + threadIdx.x * 8 + e;
+      *dst = bias_accumulate ? *dst + s : s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Head backward pointwise: dlogit = dy * y * (1 - y) * scale, gathered into the "col" tensor
+//   G[(t*B + b)][h][w][k = tap*C + co] = dlogit[b][co][t][h - (dy-1)][w - (dx-1)]   (zero outside)
+// which is the A operand of both the head dgrad (plain GEMM) and the head wgrad.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void head_grad_col_kernel(const float* __restrict__ dyv, const float* __restrict__ y,
+                                     E* __restrict__ G, int B, int C, int T, int H, int W, int KG, int t0, int nt,
+                                     const float* __restrict__ scale_ptr) {
+  // Only time steps [t0, t0 + nt) are gathered: G is [nt*B][H][W][KG].
+  const float scale = *scale_ptr;
+  const int chunks = KG / 8;
+  const size_t total = static_cast<size_t>(nt) * B * H * W * chunks;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ck = static_cast<int>(i % chunks);
+    size_t pix = i / chunks;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    pix /= H;
+    const int b = static_cast<int>(pix % B);
+    const int t = t0 + static_cast<int>(pix / B);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = ck * 8 + e;
+      float val = 0.f;
+      if (k < 9 * C) {
+        const int tap = k / C, co = k % C;
+        const int hy = h - (tap / 3 - 1), wx = w - (tap % 3 - 1);
+        if (hy >= 0 && hy < H && wx >= 0 && wx < W) {
+          const size_t idx = (((static_cast<size_t>(b) * C + co) * T + t) * H + hy) * W + wx;
+          const float yy = __ldg(y + idx);
+          val = __ldg(dyv + idx) * yy * (1.f - yy) * scale;
+        }
+      }
+      v[e] = val;
+    }
+    reinterpret_cast<uint4*>(G)[i] = make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]),
+                                                Elem<E>::pack2(v[4], v[5]), Elem<E>::pack2(v[6], v[7]));
+  }
+}
+
+// head bias gradient: db[co] = sum dy*y*(1-y).  grid = (chunks, C); partial[co][chunk], fixed order.
+__global__ void __launch_bounds__(256)
+head_bias_partial_kernel(const float* __restrict__ dyv, const float* __restrict__ y, float* __restrict__ partial,
+                         int B, int C, int T, int H, int W) {
+  const int co = blockIdx.y;
+  const size_t per_b = static_cast<size_t>(T) * H * W;
+  const size_t total = static_cast<size_t>(B) * per_b;
+  float s = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / per_b, r = i % per_b;
+    const size_t idx = (b * C + co) * per_b + r;
+    const float yy = __ldg(y + idx);
+    s += __ldg(dyv + idx) * yy * (1.f - yy);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[static_cast<size_t>(co) * gridDim.x + blockIdx.x] = red[0];
+}
+
+// out[i] = scale * sum_r partial[r*stride_r + idx(i)]   generic strided split reduction
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int rows,
+                                   size_t row_stride, size_t elem_stride, float scale, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += partial[r * row_stride + i * elem_stride];
+  s *= scale;
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+// Cell bias gradient: db_ref[gate*hid + j] = scale * sum_blocks partial[blk][gate*HP + j]
+__global__ void cell_bias_finalize_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks,
+                                          int hid, int HP, const float* __restrict__ scale_ptr, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * hid) return;
+  const float scale = *scale_ptr;
+  const int gate = i / hid, j = i % hid;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * 4 * HP + gate * HP + j];
+  s *= scale;
+  db[i] = accumulate ? db[i] + s : s;
+}
+
+// Cell weight gradient: dW_ref[n_ref][c_full][tap] = scale * sum_splits D[s][gate*HP + j][k(c_full,tap)]
+__global__ void cell_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, CellGeom g,
+                                           int splits, const float* __restrict__ scale_ptr, int accumulate) {
+  const float scale = *scale_ptr;
+  const int taps = g.kh * g.kw;
+  const int ctot = g.cin + g.hid;
+  const size_t total = static_cast<size_t>(4 * g.hid) * ctot * taps;
+  const size_t K = static_cast<size_t>(g.KIN) + taps * g.HP;
+  const size_t split_stride = static_cast<size_t>(4 * g.HP) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int c_full = static_cast<int>((i / taps) % ctot);
+    const int n_ref = static_cast<int>(i / (static_cast<size_t>(taps) * ctot));
+    const int gate = n_ref / g.hid, j = n_ref % g.hid;
+    size_t k;
+    if (c_full < g.cin)
+      k = g.in_col ? static_cast<size_t>(tap) * g.cin + c_full : static_cast<size_t>(tap) * g.CIP + c_full;
+    else
+      k = static_cast<size_t>(g.KIN) + static_cast<size_t>(tap) * g.HP + (c_full - g.cin);
+    const float* src = partial + static_cast<size_t>(gate * g.HP + j) * K + k;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
+    s *= scale;
+    dw[i] = accumulate ? dw[i] + s : s;
+  }
+}
+
+// Head weight gradient: dWhead[co][c][tap] = scale * sum_splits D[s][tap*C + co][c]   (D rows KG, cols HP)
+__global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int c_out,
+                                           int hid, int HP, int KG, int splits, const float* __restrict__ scale_ptr,
+                                           int accumulate) {
+  const int total = c_out * hid * 9;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float scale = *scale_ptr;
+  const int tap = i % 9, c = (i / 9) % hid, co = i / (9 * hid);
+  const float* src = partial + static_cast<size_t>(tap * c_out + co) * HP + c;
+  const size_t split_stride = static_cast<size_t>(KG) * HP;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
+  s *= scale;
+  dw[i] = accumulate ? dw[i] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Loss-scale selection for 16-bit gradient operands.  amax_bits <- max |dy*y*(1-y)| (as float bits;
+// non-negative floats order like unsigned ints), then scale[0] = S = 2^floor(log2(target/amax)),
+// scale[1] = 1/S.  Everything stays on the device: no host synchronisation.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_grad_amax_kernel(const float* __restrict__ dyv, const float* __restrict__ y, size_t n,
+                      unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float yy = __ldg(y + i);
+    m = fmaxf(m, fabsf(__ldg(dyv + i) * yy * (1.f - yy)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wv = 1; wv < 8; ++wv) m = fmaxf(m, red[wv]);
+    if (m > 0.f && m < 3.0e38f) atomicMax(amax_bits, __float_as_uint(m));
+  }
+}
+
+// amax_bits <- max(amax_bits, max |a|)
+__global__ void __launch_bounds__(256)
+abs_amax_kernel(const float* __restrict__ a, size_t n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(a + i)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int wv = 1; wv < 8; ++wv) m = fmaxf(m, red[wv]);
+    if (m > 0.f && m < 3.0e38f) atomicMax(amax_bits, __float_as_uint(m));
+  }
+}
+
+__global__ void choose_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale,
+                                    float target, float fixed) {
+  float s = fixed;
+  if (!(fixed > 0.f)) {
+    const float amax = __uint_as_float(*amax_bits);
+    s = 1.f;
+    if (amax > 0.f) s = exp2f(floorf(log2f(target / amax)));
+    s = fminf(fmaxf(s, 1.0e-30f), 1.0e30f);
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+}
+
+}  // namespace clstm

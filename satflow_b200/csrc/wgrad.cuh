@@ -1,0 +1,198 @@
+// Weight-gradient GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[n, (j, c)] = sum over pixels p:  A[p, n] * B_j[p + shift_j, c]
+//
+// A  = gate pre-activation gradients dz (or the head's dlogit "col" tensor), NHWC fp16/bf16.
+// B_j = one 64-channel chunk of an activation tensor, shifted by tap j (again a TMA coordinate shift
+//       with out-of-bounds zero fill == the convolution's zero padding).
+// Both operands are read from their NHWC layout, i.e. the GEMM's K dimension (pixels) is the slow
+// one in shared memory, so both are described to the tensor core as MN-major (128-B swizzle).
+// Each CTA owns (one 128-row block of n) x (one group of <= 8 column blocks) x (one split of the
+// pixel range): its [128 x 64*nb] fp32 accumulator stays in TMEM for the whole K loop and is then
+// added into its private slice partial[split] -- deterministic, no atomics; a finalize kernel
+// reduces the splits (pointwise.cuh).
+#pragma once
+#include "ptx.cuh"
+
+namespace clstm {
+
+constexpr int kWgTileP = 64;  // pixels per K step
+constexpr int kWgMaxGroupBlocks = 8;
+constexpr int kWgThreads = 256;
+
+// Column blocks of one operand tensor: block j -> tap j / chunks (row-major over (kh, kw)), 64-channel
+// chunk j % chunks.  A "direct" segment has kw == 1, cy == cx == 0 and a single tap.
+struct WgradSeg {
+  int nblk;    // taps * chunks
+  int chunks;  // 64-channel chunks of the tensor
+  int kw;      // taps per filter row
+  int cy, cx;  // filter centre (kh/2, kw/2)
+  int b_off;   // image offset into the segment's tensor map
+};
+
+struct WgradParams {
+  int B, H, W;
+  int BW, BH;  // pixel tile of a K step, BW*BH == 64
+  int tiles_w, tiles_h, num_p_tiles;
+  int n_blocks;     // 128-channel blocks of A
+  int group_size;   // column blocks per CTA (<= kWgMaxGroupBlocks)
+  int total_blocks;
+  WgradSeg seg[2];  // seg[1].nblk may be 0
+  int a_b_off;      // image offset into the A map
+  int splits;
+  int stages;
+  float* partial;  // [splits][n_blocks*128][total_blocks*64] fp32
+  int accumulate;  // 0: overwrite, 1: +=
+};
+
+template <typename E>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ CUtensorMap tmB1, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  int idx = blockIdx.x;
+  const int split = idx % p.splits;
+  idx /= p.splits;
+  const int nb = idx % p.n_blocks;
+  const int grp = idx / p.n_blocks;
+  const int blk0 = grp * p.group_size;
+  const int nblk = min(p.group_size, p.total_blocks - blk0);
+
+  constexpr int kBoxBytes = kWgTileP * 128;  // one 64-channel x 64-pixel box
+  const int stage_bytes = (2 + nblk) * kBoxBytes;
+  uint8_t* tail = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tmB1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's K range: pixel tiles split, split+splits, ...
+  const int my_tiles = (p.num_p_tiles - split + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int pt = split + it * p.splits;
+        const int tw = pt % p.tiles_w;
+        const int th = (pt / p.tiles_w) % p.tiles_h;
+        const int b = pt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        tma_load_4d(dst, &tmA, &full_bar[stage], nb * 128, w0, h0, b + p.a_b_off);
+        tma_load_4d(dst + kBoxBytes, &tmA, &full_bar[stage], nb * 128 + 64, w0, h0, b + p.a_b_off);
+        for (int j = 0; j < nblk; ++j) {
+          int jj = blk0 + j;
+          const int sidx = (jj < p.seg[0].nblk) ? 0 : 1;
+          if (sidx) jj -= p.seg[0].nblk;
+          const WgradSeg sg = p.seg[sidx];
+          const int tap = jj / sg.chunks, chunk = jj % sg.chunks;
+          tma_load_4d(dst + (2 + j) * kBoxBytes, sidx == 0 ? &tmB0 : &tmB1, &full_bar[stage], chunk * 64,
+                      w0 + tap % sg.kw - sg.cx, h0 + tap / sg.kw - sg.cy, b + sg.b_off);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128 (two 64-channel MN groups, LBO apart), N = 64, both operands MN-major.
+      const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t base = smem_u32(smem + stage * stage_bytes);
+        const uint64_t adesc = make_smem_desc_sw128(base, kBoxBytes, 1024);
+        for (int j = 0; j < nblk; ++j) {
+          const uint64_t bdesc = make_smem_desc_sw128(base + (2 + j) * kBoxBytes, kBoxBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kWgTileP / 16; ++k) {
+            // K = 16 pixels = 16 rows of 128 B = 2048 B per step (start-address field in 16-B units)
+            umma_f16(tmem_base + j * 64, adesc + k * 128, bdesc + k * 128, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // n within the block
+    if (my_tiles > 0) {
+      mbar_wait(done_bar, 0);
+      tcgen05_fence_after();
+    }
+    const size_t ld = static_cast<size_t>(p.total_blocks) * 64;
+    float* dst_row = p.partial + (static_cast<size_t>(split) * p.n_blocks * 128 + nb * 128 + row) * ld +
+                     static_cast<size_t>(blk0) * 64;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int g = 0; g < nblk * 4; ++g) {
+      uint32_t v[16];
+      if (my_tiles > 0) {
+        tmem_ld16(taddr + g * 16, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0;
+      }
+      float4* d4 = reinterpret_cast<float4*>(dst_row + g * 16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float4 o = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                               __uint_as_float(v[4 * e + 3]));
+        if (p.accumulate) {
+          float4 old = d4[e];
+          o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+        }
+        d4[e] = o;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline size_t wgrad_smem_bytes(int stages, int max_group_blocks) {
+  return 1024 + static_cast<size_t>(stages) * (2 + max_group_blocks) * (kWgTileP * 128) + 17 * 8 + 16 + 64;
+}
+
+}  // namespace clstm

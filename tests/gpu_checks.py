@@ -1,0 +1,142 @@
+"""Shared parity checks: CUDA path (through the C ABI) vs the CPU fp32 oracle / golden fixtures.
+Each returns {tensor name: rel-L2}; the tests assert the tolerance, tools/gpu_check.py prints them."""
+from __future__ import annotations
+
+import os
+from typing import Dict
+
+import numpy as np
+import torch
+
+from oracle import convlstm_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 2e-3  # BASELINE.json north_star: relative-L2 <= 2e-3 per tensor
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    return O.rel_l2(a.detach().cpu().float(), b.detach().cpu().float())
+
+
+def load_golden(name: str) -> Dict[str, torch.Tensor]:
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+def cell_case(B, cin, hid, H, W, kh, kw, dtype="fp16", seed=0, backward=True) -> Dict[str, float]:
+    from satflow_b200 import ConvLSTMCell
+
+    g = torch.Generator().manual_seed(seed)
+    cell = ConvLSTMCell(cin, hid, (kh, kw), True)
+    cell.operand_dtype = dtype
+    x = torch.randn(B, cin, H, W, generator=g)
+    h = torch.randn(B, hid, H, W, generator=g) * 0.5
+    c = torch.randn(B, hid, H, W, generator=g)
+    dh = torch.randn(B, hid, H, W, generator=g)
+    dc = torch.randn(B, hid, H, W, generator=g)
+    w = cell.conv.weight.detach().clone()
+    b = cell.conv.bias.detach().clone()
+    # oracle
+    xo, ho, co = (t.clone().requires_grad_(True) for t in (x, h, c))
+    wo, bo = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    hn_o, cn_o, _ = O.cell_forward(xo, ho, co, wo, bo)
+    out: Dict[str, float] = {}
+    cell = cell.cuda()
+    xg, hg, cg = (t.cuda().requires_grad_(True) for t in (x, h, c))
+    hn, cn = cell(xg, [hg, cg])
+    out["h_next"] = rel(hn, hn_o)
+    out["c_next"] = rel(cn, cn_o)
+    if backward:
+        (hn_o * dh + cn_o * dc).sum().backward()
+        (hn * dh.cuda() + cn * dc.cuda()).sum().backward()
+        out["dx"] = rel(xg.grad, xo.grad)
+        out["dh_cur"] = rel(hg.grad, ho.grad)
+        out["dc_cur"] = rel(cg.grad, co.grad)
+        out["dweight"] = rel(cell.conv.weight.grad, wo.grad)
+        out["dbias"] = rel(cell.conv.bias.grad, bo.grad)
+    return out
+
+
+def cell_golden(name: str, dtype="fp16") -> Dict[str, float]:
+    from satflow_b200 import ConvLSTMCell
+
+    z = load_golden(name)
+    hid = z["h"].shape[1]
+    cin = z["x"].shape[1]
+    kh, kw = z["weight"].shape[2:]
+    cell = ConvLSTMCell(cin, hid, (kh, kw), True)
+    cell.operand_dtype = dtype
+    cell.load_state_dict({"conv.weight": z["weight"], "conv.bias": z["bias"]})
+    cell = cell.cuda()
+    xg, hg, cg = (z[k].cuda().requires_grad_(True) for k in ("x", "h", "c"))
+    hn, cn = cell(xg, [hg, cg])
+    (hn * z["dh"].cuda() + cn * z["dc"].cuda()).sum().backward()
+    return {
+        "h_next": rel(hn, z["h_next"]), "c_next": rel(cn, z["c_next"]), "dx": rel(xg.grad, z["dx"]),
+        "dh_cur": rel(hg.grad, z["dh_cur"]), "dc_cur": rel(cg.grad, z["dc_cur"]),
+        "dweight": rel(cell.conv.weight.grad, z["dweight"]), "dbias": rel(cell.conv.bias.grad, z["dbias"]),
+    }
+
+
+def rollout_case(B, tin, tout, cin, hid, cout, H, W, n_layers=2, k=3, dtype="fp16", weight_scale=1.0, seed=0,
+                 backward=True, states=True) -> Dict[str, float]:
+    """CUDA rollout (module API -> C ABI) vs the oracle on the same seeded inputs and weights."""
+    from satflow_b200 import ConvLSTM
+
+    g = torch.Generator().manual_seed(1234 + seed)
+    p = O.init_params(cin, hid, cout, n_layers=n_layers, kernel_size=(k, k), seed=seed, cell_weight_scale=weight_scale)
+    x = torch.randn(B, tin, cin, H, W, generator=g)
+    tgt = torch.rand(B, tout, cout, H, W, generator=g)
+    y_o, sv = O.rollout_forward(x, p, tout, n_layers=n_layers)
+    net = ConvLSTM(cin, hid, cout, n_layers=n_layers, kernel_size=(k, k), operand_dtype=dtype)
+    net.load_state_dict(p)
+    net = net.cuda()
+    out: Dict[str, float] = {}
+    if backward:
+        y = net(x.cuda(), tout)
+        loss = torch.nn.functional.mse_loss(y.permute(0, 2, 1, 3, 4), tgt.cuda())
+        loss.backward()
+        loss_o, dy_o = O.mse_loss_and_grad(y_o, tgt)
+        g_o = O.rollout_backward(dy_o, sv, p)
+        out["loss"] = abs(loss.item() - loss_o.item()) / abs(loss_o.item())
+        for name, prm in net.named_parameters():
+            out["grad." + name] = rel(prm.grad, g_o[name])
+    else:
+        with torch.no_grad():
+            y = net(x.cuda(), tout)
+    out["y"] = rel(y, y_o)
+    # pre-sigmoid logits are the sensitive forward signal
+    yc = y.detach().cpu().double().clamp(1e-12, 1 - 1e-12)
+    out["logits"] = rel(torch.log(yc / (1 - yc)).float(), sv.logits)
+    if states:
+        plan = next(iter(net._plans.values()))
+        ncell = 2 * n_layers
+        for cidx in range(ncell):
+            T = tin if cidx < n_layers else tout
+            h, c = plan.read_state(cidx, T)
+            out[f"h_final[{cidx}]"] = rel(h, sv.final_h[cidx])
+            out[f"c_final[{cidx}]"] = rel(c, sv.final_c[cidx])
+    net.release_plans()
+    return out
+
+
+def rollout_golden(name: str, dtype="fp16") -> Dict[str, float]:
+    from satflow_b200 import EncoderDecoderConvLSTM
+
+    z = load_golden(name)
+    x, tgt = z["x"], z["target"]
+    hid = z["param.model.encoder_1_convlstm.conv.bias"].numel() // 4
+    cout = z["param.model.decoder_CNN.bias"].numel()
+    lit = EncoderDecoderConvLSTM(hidden_dim=hid, input_channels=x.shape[2], out_channels=cout, forecast_steps=tgt.shape[1])
+    lit.model.operand_dtype = dtype
+    lit.load_state_dict({k[len("param."):]: v for k, v in z.items() if k.startswith("param.")})
+    lit = lit.cuda()
+    loss = lit.training_step((x.cuda(), tgt.cuda()), 0)
+    loss.backward()
+    with torch.no_grad():
+        y = lit(x.cuda(), tgt.shape[1])
+    out = {"y": rel(y, z["y"]), "loss": abs(loss.item() - float(z["loss"])) / float(z["loss"])}
+    for k, prm in lit.named_parameters():
+        out["grad." + k] = rel(prm.grad, z["grad." + k])
+    lit.model.release_plans()
+    return out
