@@ -104,6 +104,11 @@ int clstm_rollout_backward(clstm_plan_t* plan, const float* dy, const float* y, 
  * Either output may be NULL.  In inference plans only the last two c steps are retained. */
 int clstm_plan_read_state(clstm_plan_t* plan, int cell, int step, float* h_out, float* c_out, void* stream);
 
+/* Measurement hook: re-launches exactly the fused cell-step kernel that clstm_rollout_forward issues for
+ * (cell, step), on the plan's own tensors (the step is idempotent: same inputs, same outputs), so a
+ * caller can bracket N launches of the dominant kernel with CUDA events on `stream` (bench.py roofline). */
+int clstm_plan_profile_cell_step(clstm_plan_t* plan, int cell, int step, void* stream);
+
 /* ---- single cell step: ConvLSTMCell.forward (layers/ConvLSTM.py:42-57) and its backward ------
  * A cell plan is a rollout plan restricted to one cell and one step; tensors use the reference
  * layout: x (B,Cin,H,W), h/c (B,hid,H,W), weight (4*hid, Cin+hid, kh, kw), bias (4*hid) or NULL. */

@@ -830,11 +830,13 @@ int cellplan_backward(clstm_cell_plan* p, const float* dh_next, const float* dc_
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   if (dh_cur) {
-    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dh_own, dh_cur, geo.B, p->hid, geo.H, geo.W, HP, nullptr, 0);
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dh_own, dh_cur, geo.B, p->hid, geo.H, geo.W, HP,
+                                                           ctx.scale + 1, 0);
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   if (dc_cur) {
-    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dc, dc_cur, geo.B, p->hid, geo.H, geo.W, HP, nullptr, 0);
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.dc, dc_cur, geo.B, p->hid, geo.H, geo.W, HP,
+                                                           ctx.scale + 1, 0);
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   return 0;
@@ -1010,6 +1012,25 @@ int clstm_plan_read_state(clstm_plan_t* p, int cell, int step, float* h_out, flo
     return fail(CLSTM_ESTATE, "inference plans keep only the last two c steps of cell %d", cell);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL_(E) plan_read_state<E>(p, cell, step, h_out, c_out, st)
+  return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_plan_profile_cell_step(clstm_plan_t* p, int cell, int step, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "profile_cell_step before forward");
+  if (cell < 0 || cell >= p->ncell) return fail(CLSTM_EINVAL, "cell index %d out of range", cell);
+  CellState& cs = p->cells[cell];
+  if (step < 0 || step >= cs.T) return fail(CLSTM_EINVAL, "step %d out of range [0,%d)", step, cs.T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t npix = p->ctx.geo.npix();
+  const int HP = p->ctx.HP;
+  const InputRef in = plan_input(p, cell, step);
+  const float* c_prev = (step == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, step)) * npix * HP;
+  float* c_next = cs.c + static_cast<size_t>(cslot(cs, step + 1)) * npix * HP;
+  void* gates = nullptr;
+  if (p->cfg.training) gates = static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(step) * npix * 4 * HP * 2;
+#define CALL_(E) cell_forward_step<E>(p->ctx, cs, in, hslot(cs, step), hslot(cs, step + 1), c_prev, c_next, gates, st)
   return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
 }

@@ -124,6 +124,11 @@ class RolloutPlan:
                 )
             )
 
+    def profile_cell_step(self, cell: int, step: int) -> None:
+        """Re-launch the fused cell-step kernel of (cell, step) (measurement hook, include/clstm.h)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().clstm_plan_profile_cell_step(self._h, cell, step, _stream_ptr(self.device)))
+
     def read_state(self, cell: int, step: int):
         c = self.cfg
         h = torch.empty(c.batch, c.hidden, c.height, c.width, dtype=torch.float32, device=self.device)

@@ -1,0 +1,124 @@
+"""CPU: the C-ABI library loads and exports every symbol include/clstm.h declares; host-side validation
+and the drop-in Python surface (registry, constructors, state_dict layout) behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import satflow_b200 as S
+from satflow_b200 import _lib
+from gpu_checks import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "clstm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(clstm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_lib.exported_symbols()) == declared
+    assert L.clstm_abi_version() == 1
+
+
+def _create(**kw):
+    base = dict(batch=2, height=16, width=16, in_channels=12, hidden=32, out_channels=12, n_layers=2, kernel_h=3,
+                kernel_w=3, t_in=4, t_out=4, dtype=0, training=1, grad_scale=0.0)
+    base.update(kw)
+    cfg = _lib.Config(*[base[f[0]] for f in _lib.Config._fields_])
+    h = ctypes.c_void_p()
+    rc = _lib.lib().clstm_plan_create(ctypes.byref(cfg), ctypes.byref(h))
+    return rc, h
+
+
+def test_plan_create_validates_without_a_gpu():
+    L = _lib.lib()
+    rc, h = _create()
+    assert rc == 0 and h.value
+    ws_train = L.clstm_plan_workspace_bytes(h)
+    L.clstm_plan_destroy(h)
+    rc, h = _create(training=0)
+    ws_inf = L.clstm_plan_workspace_bytes(h)
+    L.clstm_plan_destroy(h)
+    assert 0 < ws_inf < ws_train
+    for bad in (dict(t_out=0), dict(kernel_h=4), dict(hidden=1024), dict(batch=0), dict(dtype=7), dict(n_layers=0)):
+        rc, _ = _create(**bad)
+        assert rc == -1, bad
+        assert L.clstm_last_error()
+    rc, _ = _create(t_out=0)
+    assert b"forecast_steps" in L.clstm_last_error()
+
+
+def test_workspace_scales_with_saved_states():
+    L = _lib.lib()
+    sizes = []
+    for t_out in (2, 4):
+        rc, h = _create(t_out=t_out)
+        sizes.append(L.clstm_plan_workspace_bytes(h))
+        L.clstm_plan_destroy(h)
+    npix, HP = 2 * 16 * 16, 64
+    per_step = 2 * (npix * HP * 2 + npix * HP * 4 + npix * 4 * HP * 2)  # two decoder cells: h + c + gates
+    assert sizes[1] - sizes[0] >= 2 * per_step
+    assert sizes[1] - sizes[0] < 2 * per_step + 64 * 1024
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    assert _lib.lib().clstm_device_check(0) == -3
+    m = S.ConvLSTM(12, 8, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.randn(1, 2, 12, 8, 8), 2)
+    cell = S.ConvLSTMCell(3, 4, (3, 3), True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cell(torch.randn(1, 3, 8, 8), cell.init_hidden(1, (8, 8)))
+
+
+def test_registry_mirrors_reference_contract():
+    # reference tests/test_models.py:64-75: every registered name constructs with no kwargs
+    assert "encoderdecoderconvlstm" in S.list_models()
+    for name in S.list_models():
+        assert S.create_model(name) is not None
+    assert S.get_model("EncoderDecoderConvLSTM") is S.EncoderDecoderConvLSTM
+    with pytest.raises(KeyError):
+        S.get_model("nope")
+
+
+def test_constructor_defaults_and_from_config():
+    m = S.EncoderDecoderConvLSTM()
+    assert (m.forecast_steps, m.lr, m.model.hidden_dim, m.model.input_channels, m.model.out_channels) == (48, 0.001, 64, 12, 1)
+    assert isinstance(m.criterion, torch.nn.MSELoss)
+    m2 = S.EncoderDecoderConvLSTM.from_config({"num_hidden": 8, "in_channels": 3})
+    assert (m2.forecast_steps, m2.model.hidden_dim, m2.model.input_channels) == (1, 8, 3)  # conv_lstm.py:41 default 1
+    assert isinstance(m.configure_optimizers(), torch.optim.Adam)
+    with pytest.raises(ValueError):
+        S.get_conv_layer("bogus")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 12, 4, 4), 0)  # future_seq = 0 raises like the reference
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    z = load_golden("rollout_h16_12x10")
+    ref = {k[len("param."):]: v for k, v in z.items() if k.startswith("param.")}
+    m = S.EncoderDecoderConvLSTM(hidden_dim=16, input_channels=12, out_channels=5, forecast_steps=4)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    m.load_state_dict(ref)  # strict
+    bare = S.ConvLSTM(12, 16, 5)
+    assert list(bare.state_dict().keys()) == [k[len("model."):] for k in ref]
+    cell = bare.encoder_1_convlstm
+    assert (cell.input_dim, cell.hidden_dim, cell.kernel_size, cell.padding, cell.bias) == (12, 16, (3, 3), (1, 1), True)
+    h, c = cell.init_hidden(2, (5, 7))
+    assert h.shape == (2, 16, 5, 7) and float(h.abs().sum() + c.abs().sum()) == 0.0
+    # CloudGAN's init_net matches sub-modules whose class name contains "Conv" and that own .weight (gan/common.py:46-64)
+    assert "Conv" in type(cell.conv).__name__ and hasattr(cell.conv, "weight")
