@@ -104,10 +104,17 @@ int clstm_rollout_backward(clstm_plan_t* plan, const float* dy, const float* y, 
  * Either output may be NULL.  In inference plans only the last two c steps are retained. */
 int clstm_plan_read_state(clstm_plan_t* plan, int cell, int step, float* h_out, float* c_out, void* stream);
 
-/* Measurement hook: re-launches exactly the fused cell-step kernel that clstm_rollout_forward issues for
- * (cell, step), on the plan's own tensors (the step is idempotent: same inputs, same outputs), so a
- * caller can bracket N launches of the dominant kernel with CUDA events on `stream` (bench.py roofline). */
-int clstm_plan_profile_cell_step(clstm_plan_t* plan, int cell, int step, void* stream);
+/* Measurement hook: re-launches exactly one of the kernels that the rollout issues for (cell, step), on the
+ * plan's own tensors, so a caller can bracket N launches with CUDA events on `stream` (bench.py roofline,
+ * tools/kernel_bench.py).  CELL_FWD is idempotent; the backward kinds reuse whatever the last backward left
+ * in the scratch tensors (timing only; gate-grad updates dc in place, wgrad accumulates into its partials). */
+enum {
+  CLSTM_KERNEL_CELL_FWD = 0,  /* fused conv + LSTM epilogue (layers/ConvLSTM.py:45-55) */
+  CLSTM_KERNEL_GATE_GRAD = 1, /* pointwise gate gradient */
+  CLSTM_KERNEL_DGRAD = 2,     /* data gradient GEMM */
+  CLSTM_KERNEL_WGRAD = 3      /* weight gradient GEMM */
+};
+int clstm_plan_profile_kernel(clstm_plan_t* plan, int kind, int cell, int step, void* stream);
 
 /* ---- single cell step: ConvLSTMCell.forward (layers/ConvLSTM.py:42-57) and its backward ------
  * A cell plan is a rollout plan restricted to one cell and one step; tensors use the reference

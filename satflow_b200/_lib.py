@@ -56,7 +56,7 @@ _PROTOTYPES = {
     "clstm_rollout_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_rollout_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p]),
     "clstm_plan_read_state": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "clstm_plan_profile_cell_step": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "clstm_plan_profile_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "clstm_cell_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "clstm_cell_plan_destroy": (c_int, [c_void_p]),
     "clstm_cell_plan_workspace_bytes": (c_size_t, [c_void_p]),

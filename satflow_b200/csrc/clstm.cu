@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -55,6 +56,12 @@ inline int after_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(CLSTM_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   return 0;
+}
+
+// Experiment knobs (read once): integer environment variables, used by tools/kernel_bench.py sweeps.
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -229,7 +236,9 @@ struct Carver {
 
 void wgrad_shape(const DeviceInfo& dev, int total_blocks, int n_blocks, long long p_tiles, int* group_size,
                  int* splits) {
-  int groups = (total_blocks + kWgMaxGroupBlocks - 1) / kWgMaxGroupBlocks;
+  int max_group = env_int("CLSTM_WG_GROUP", kWgMaxGroupBlocks);
+  if (max_group < 1 || max_group > kWgMaxGroupBlocks) max_group = kWgMaxGroupBlocks;
+  int groups = (total_blocks + max_group - 1) / max_group;
   int gs = (total_blocks + groups - 1) / groups;
   groups = (total_blocks + gs - 1) / gs;
   int sms = dev.sms > 0 ? dev.sms : 148;
@@ -336,6 +345,23 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   return after_launch("wgrad_kernel");
 }
 
+// Row-tiled im2col when its shared-memory tile fits, else the generic gather kernels.
+template <typename E, int MODE>
+int launch_row_im2col(const float* s0, const float* s1, E* out, int B, int T, int C, int H, int W, int kh, int kw,
+                      int KP, int t0, int nt, const float* scale_ptr, cudaStream_t st, bool* used) {
+  const size_t smem = row_im2col_smem_bytes(C, W, kh, kw, KP);
+  *used = false;
+  if (smem > 160 * 1024 || static_cast<long long>(nt) * B * H > 0x7fffffffll) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(row_im2col_kernel<E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  row_im2col_kernel<E, MODE><<<nt * B * H, 256, smem, st>>>(s0, s1, out, B, T, C, H, W, kh, kw, KP, t0, scale_ptr);
+  *used = true;
+  return after_launch("row_im2col_kernel");
+}
+
 // --------------------------------------------------------------------------- cell building blocks
 // Repack one cell's reference-layout parameters (layers/ConvLSTM.py:34-40 weight/bias).
 template <typename E>
@@ -371,59 +397,72 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.h_next = static_cast<E*>(cs.h) + static_cast<size_t>(sn) * cs.h_slot_elems(ctx.geo);
   p.gates = gates;
   p.ldc = ctx.HP;
+  p.act_mode = env_int("CLSTM_ACT_MODE", 0);
   return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
 }
 
-// Backward of one cell step: fused gate gradient -> dgrad (dx | dh_prev) -> wgrad accumulation.
-// dh sources (fp32 NHWC, scaled by S) may be null.  c_prev may be null (zeros).
+// Backward of one cell step, three launches: fused gate gradient -> dgrad (dx | dh_prev) -> wgrad
+// accumulation.  dh sources (fp32 NHWC, scaled by S) may be null.  c_prev may be null (zeros).
+template <typename E>
+int cell_gate_grad(const Ctx& ctx, CellState& cs, const void* gates, const float* c_prev, const float* c_next,
+                   const float* dh0, const float* dh1, const float* dh2, int first, cudaStream_t st) {
+  // pointwise gate gradient (backward of layers/ConvLSTM.py:48-55)
+  gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 33 * sizeof(float), st>>>(
+      static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dz), cs.bpart, !first,
+      ctx.geo.npix(), ctx.HP);
+  return after_launch("gate_grad_kernel");
+}
+
+template <typename E>
+int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
+  // d[x | h_prev] = conv_transpose(dz, W)  (backward of layers/ConvLSTM.py:45-47)
+  const CellGeom& g = cs.g;
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_tile = cs.n_tile_d;
+  p.n_tiles = cs.rows_d / cs.n_tile_d;
+  p.nseg = 1;
+  p.seg[0] = ConvSeg{4 * ctx.HP / 64, g.kh, g.kw, 0};
+  p.out0 = cs.dxb;
+  p.out1 = cs.dh_own;
+  p.split_col = cs.with_x ? g.CIP : 0;
+  p.ld0 = g.CIP;
+  p.ld1 = ctx.HP;
+  p.out_scale = 1.f;
+  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, ctx.geo, ctx.geo.B, st);
+}
+
+template <typename E>
+int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st) {
+  // dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
+  const CellGeom& g = cs.g;
+  const Geo& geo = ctx.geo;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_blocks = 4 * ctx.HP / 128;
+  p.group_size = cs.wg_group;
+  p.total_blocks = cs.wg_total;
+  if (g.in_col)
+    p.seg[0] = WgradSeg{g.KIN / 64, g.KIN / 64, 1, 0, 0, in.b_off};
+  else
+    p.seg[0] = WgradSeg{g.kh * g.kw * (g.CIP / 64), g.CIP / 64, g.kw, g.kh / 2, g.kw / 2, in.b_off};
+  p.seg[1] = WgradSeg{g.kh * g.kw * (ctx.HP / 64), ctx.HP / 64, g.kw, g.kh / 2, g.kw / 2, sp * geo.B};
+  p.a_b_off = 0;
+  p.splits = cs.wg_splits;
+  p.partial = cs.wpart;
+  p.accumulate = !first;
+  return launch_wgrad<E>(ctx.dev, ctx.m_dz64, *in.map64, cs.m_h64, p, geo, geo.B, st);
+}
+
 template <typename E>
 int cell_backward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, const void* gates,
                        const float* c_prev, const float* c_next, const float* dh0, const float* dh1,
                        const float* dh2, cudaStream_t st) {
-  const CellGeom& g = cs.g;
-  const Geo& geo = ctx.geo;
-  const size_t npix = geo.npix();
   const int first = cs.bwd_started ? 0 : 1;
   cs.bwd_started = true;
-  // (1) pointwise gate gradient (backward of layers/ConvLSTM.py:48-55)
-  gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 33 * sizeof(float), st>>>(
-      static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dz), cs.bpart, !first,
-      npix, ctx.HP);
-  RC_TRY(after_launch("gate_grad_kernel"));
-  // (2) dgrad: d[x | h_prev] = conv_transpose(dz, W)  (backward of :45-47)
-  {
-    ConvGemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.n_tile = cs.n_tile_d;
-    p.n_tiles = cs.rows_d / cs.n_tile_d;
-    p.nseg = 1;
-    p.seg[0] = ConvSeg{4 * ctx.HP / 64, g.kh, g.kw, 0};
-    p.out0 = cs.dxb;
-    p.out1 = cs.dh_own;
-    p.split_col = cs.with_x ? g.CIP : 0;
-    p.ld0 = g.CIP;
-    p.ld1 = ctx.HP;
-    p.out_scale = 1.f;
-    RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, geo, geo.B, st)));
-  }
-  // (3) wgrad: dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
-  {
-    WgradParams p;
-    memset(&p, 0, sizeof(p));
-    p.n_blocks = 4 * ctx.HP / 128;
-    p.group_size = cs.wg_group;
-    p.total_blocks = cs.wg_total;
-    if (g.in_col)
-      p.seg[0] = WgradSeg{g.KIN / 64, g.KIN / 64, 1, 0, 0, in.b_off};
-    else
-      p.seg[0] = WgradSeg{g.kh * g.kw * (g.CIP / 64), g.CIP / 64, g.kw, g.kh / 2, g.kw / 2, in.b_off};
-    p.seg[1] = WgradSeg{g.kh * g.kw * (ctx.HP / 64), ctx.HP / 64, g.kw, g.kh / 2, g.kw / 2, sp * geo.B};
-    p.a_b_off = 0;
-    p.splits = cs.wg_splits;
-    p.partial = cs.wpart;
-    p.accumulate = !first;
-    RC_TRY((launch_wgrad<E>(ctx.dev, ctx.m_dz64, *in.map64, cs.m_h64, p, geo, geo.B, st)));
-  }
+  RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, dh0, dh1, dh2, first, st));
+  RC_TRY(cell_dgrad<E>(ctx, cs, st));
+  RC_TRY(cell_wgrad<E>(ctx, cs, in, sp, first, st));
   return 0;
 }
 
@@ -557,9 +596,14 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
   const int HP = ctx.HP;
   const int L = p->L;
   // x (B,T,C,H,W) -> im2col'd 16-bit tensor, once for all T_in steps
-  pack_xcol_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels,
-                                                   c.height, c.width, c.kernel_h, c.kernel_w, p->KX);
-  RC_TRY(after_launch("pack_xcol_kernel"));
+  bool tiled = false;
+  RC_TRY((launch_row_im2col<E, 0>(x, nullptr, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels, c.height,
+                                  c.width, c.kernel_h, c.kernel_w, p->KX, 0, c.t_in, nullptr, st, &tiled)));
+  if (!tiled) {
+    pack_xcol_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels,
+                                                     c.height, c.width, c.kernel_h, c.kernel_w, p->KX);
+    RC_TRY(after_launch("pack_xcol_kernel"));
+  }
   if (!c.training) {
     // ring-buffered states: slot 0 must read as the zero initial state (layers/ConvLSTM.py:59-64)
     for (int k = 0; k < p->ncell; ++k) CU_TRY(cudaMemsetAsync(p->cells[k].h, 0, npix * HP * 2, st));
@@ -650,9 +694,14 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   const float* dfeed = nullptr;  // grad wrt the decoder input of step t + 1
   for (int t = c.t_out - 1; t >= 0; --t) {
     // head backward for this output frame: dlogit "col" tensor -> dgrad into dstack, wgrad accumulation
-    head_grad_col_kernel<E><<<kPackBlocks, 256, 0, st>>>(dy, y, static_cast<E*>(p->G), c.batch, c.out_channels,
-                                                         c.t_out, c.height, c.width, p->KG, t, 1, ctx.scale);
-    RC_TRY(after_launch("head_grad_col_kernel"));
+    bool tiled = false;
+    RC_TRY((launch_row_im2col<E, 1>(dy, y, static_cast<E*>(p->G), c.batch, c.t_out, c.out_channels, c.height, c.width,
+                                    3, 3, p->KG, t, 1, ctx.scale, st, &tiled)));
+    if (!tiled) {
+      head_grad_col_kernel<E><<<kPackBlocks, 256, 0, st>>>(dy, y, static_cast<E*>(p->G), c.batch, c.out_channels,
+                                                           c.t_out, c.height, c.width, p->KG, t, 1, ctx.scale);
+      RC_TRY(after_launch("head_grad_col_kernel"));
+    }
     {
       ConvGemmParams hp;
       memset(&hp, 0, sizeof(hp));
@@ -1016,12 +1065,14 @@ int clstm_plan_read_state(clstm_plan_t* p, int cell, int step, float* h_out, flo
 #undef CALL_
 }
 
-int clstm_plan_profile_cell_step(clstm_plan_t* p, int cell, int step, void* stream) {
+int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, void* stream) {
   if (!p) return fail(CLSTM_EINVAL, "null argument");
-  if (!p->forward_done) return fail(CLSTM_ESTATE, "profile_cell_step before forward");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "profile_kernel before forward");
   if (cell < 0 || cell >= p->ncell) return fail(CLSTM_EINVAL, "cell index %d out of range", cell);
   CellState& cs = p->cells[cell];
   if (step < 0 || step >= cs.T) return fail(CLSTM_EINVAL, "step %d out of range [0,%d)", step, cs.T);
+  if (kind != CLSTM_KERNEL_CELL_FWD && !p->cfg.training)
+    return fail(CLSTM_ESTATE, "backward kernels need a training plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t npix = p->ctx.geo.npix();
   const int HP = p->ctx.HP;
@@ -1030,9 +1081,30 @@ int clstm_plan_profile_cell_step(clstm_plan_t* p, int cell, int step, void* stre
   float* c_next = cs.c + static_cast<size_t>(cslot(cs, step + 1)) * npix * HP;
   void* gates = nullptr;
   if (p->cfg.training) gates = static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(step) * npix * 4 * HP * 2;
+  switch (kind) {
+    case CLSTM_KERNEL_CELL_FWD: {
 #define CALL_(E) cell_forward_step<E>(p->ctx, cs, in, hslot(cs, step), hslot(cs, step + 1), c_prev, c_next, gates, st)
-  return DISPATCH_E(p->cfg.dtype, CALL_);
+      return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
+    }
+    case CLSTM_KERNEL_GATE_GRAD: {
+#define CALL_(E) cell_gate_grad<E>(p->ctx, cs, gates, c_prev, c_next, cs.dh_own, p->dstack, nullptr, 0, st)
+      return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+    }
+    case CLSTM_KERNEL_DGRAD: {
+#define CALL_(E) cell_dgrad<E>(p->ctx, cs, st)
+      return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+    }
+    case CLSTM_KERNEL_WGRAD: {
+#define CALL_(E) cell_wgrad<E>(p->ctx, cs, in, hslot(cs, step), 0, st)
+      return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
+    }
+    default:
+      return fail(CLSTM_EINVAL, "unknown kernel kind %d", kind);
+  }
 }
 
 // ---------------------------------------------------------------------------- single cell

@@ -54,6 +54,8 @@ struct ConvGemmParams {
   void* h_next;         // E    [pixel][ldc]
   void* gates;          // E    [pixel][4*ldc] ([i|f|o|g] blocks of ldc) or nullptr
   int ldc;              // padded hidden channels (multiple of 64)
+  int act_mode;         // 0: one reciprocal per activation; 1: tanh.approx (experiment); 2: no MUFU (experiment);
+                        // 3: shared reciprocals (default)
   // ---- EPI_STORE
   float* out0;
   float* out1;
@@ -223,14 +225,51 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int e = 0; e < 16; ++e) cp[e] = 0.f;
             }
             float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
+            if (p.act_mode == 3) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
-              gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
-              go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
-              gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-              cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-              hn[e] = go[e] * fast_tanh(cn[e]);
+              for (int e = 0; e < 16; ++e) {
+                lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
+                                      __uint_as_float(vo[e]) + bs[128 + j0 + e],
+                                      __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+              }
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                float ta, tb;
+                tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
+                hn[e] = go[e] * ta;
+                hn[e + 1] = go[e + 1] * tb;
+              }
+            } else if (p.act_mode == 1) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                gi[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vi[e]) + bs[0 + j0 + e])), 0.5f);
+                gf[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vf[e]) + bs[64 + j0 + e])), 0.5f);
+                go[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vo[e]) + bs[128 + j0 + e])), 0.5f);
+                gg[e] = tanh_mufu(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+                hn[e] = go[e] * tanh_mufu(cn[e]);
+              }
+            } else if (p.act_mode == 2) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                gi[e] = __uint_as_float(vi[e]) + bs[0 + j0 + e];
+                gf[e] = __uint_as_float(vf[e]) + bs[64 + j0 + e];
+                go[e] = __uint_as_float(vo[e]) + bs[128 + j0 + e];
+                gg[e] = __uint_as_float(vg[e]) + bs[192 + j0 + e];
+                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+                hn[e] = go[e] * cn[e];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
+                gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
+                go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
+                gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+                hn[e] = go[e] * fast_tanh(cn[e]);
+              }
             }
             float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
 #pragma unroll

@@ -46,6 +46,78 @@ __global__ void pack_xcol_kernel(const float* __restrict__ x, E* __restrict__ xc
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-tiled im2col (the fast path of pack_xcol_kernel and head_grad_col_kernel): one block owns one
+// image row (t, b, h).  It stages the kh source rows of all C channels in shared memory once
+// (coalesced along W, converted to E), then writes the row's [W][KP] output in 16-byte chunks, fully
+// coalesced.  MODE 0: src0 = x (B,T,C,H,W), taps look forward (h + dy - kh/2).  MODE 1: the head's
+// loss gradient dy*y*(1-y)*S from src0 = dy, src1 = y (B,C,T,H,W), taps look backward (h - (dy - kh/2)),
+// which is what conv_transpose / the head wgrad need.  out is [(nt*B)][H][W][KP], k = tap*C + c.
+// ------------------------------------------------------------------------------------------
+template <typename E, int MODE>
+__global__ void __launch_bounds__(256)
+row_im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1, E* __restrict__ out, int B, int T,
+                  int C, int H, int W, int kh, int kw, int KP, int t0, const float* __restrict__ scale_ptr) {
+  extern __shared__ uint8_t rim_smem[];
+  const int WP = W + kw - 1;
+  int* lut = reinterpret_cast<int*>(rim_smem);                         // [KP] smem offset of (tap, c), or -1
+  E* sm = reinterpret_cast<E*>(rim_smem + static_cast<size_t>(KP) * 4);  // [kh][C][WP]
+  int idx = blockIdx.x;
+  const int h = idx % H;
+  idx /= H;
+  const int b = idx % B;
+  const int tt = idx / B;
+  const int t = t0 + tt;
+  const float scale = (MODE == 1) ? *scale_ptr : 1.f;
+  for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+    int off = -1;
+    if (k < kh * kw * C) {
+      const int tap = k / C, c = k % C;
+      const int dyi = tap / kw, dxi = tap % kw;
+      const int r = (MODE == 0) ? dyi : kh - 1 - dyi;
+      const int col = (MODE == 0) ? dxi : kw - 1 - dxi;
+      off = (r * C + c) * WP + col;
+    }
+    lut[k] = off;
+  }
+  const int total = kh * C * WP;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int wcol = i % WP;
+    const int c = (i / WP) % C;
+    const int r = i / (WP * C);
+    const int hy = h + r - kh / 2, wx = wcol - kw / 2;
+    float val = 0.f;
+    if (hy >= 0 && hy < H && wx >= 0 && wx < W) {
+      if (MODE == 0) {
+        val = __ldg(src0 + (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W + wx);
+      } else {
+        const size_t g = (((static_cast<size_t>(b) * C + c) * T + t) * H + hy) * W + wx;
+        const float yy = __ldg(src1 + g);
+        val = __ldg(src0 + g) * yy * (1.f - yy) * scale;
+      }
+    }
+    sm[i] = Elem<E>::from_float(val);
+  }
+  __syncthreads();
+  const int chunks = KP / 8;
+  uint4* orow = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(tt) * B + b) * H + h) * static_cast<size_t>(W) * KP);
+  const E zero = Elem<E>::from_float(0.f);
+  for (int i = threadIdx.x; i < W * chunks; i += blockDim.x) {
+    const int ck = i % chunks, w = i / chunks;
+    alignas(16) E v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int off = lut[ck * 8 + e];
+      v[e] = off >= 0 ? sm[off + w] : zero;
+    }
+    orow[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+inline size_t row_im2col_smem_bytes(int C, int W, int kh, int kw, int KP) {
+  return static_cast<size_t>(KP) * 4 + static_cast<size_t>(kh) * C * (W + kw - 1) * 2 + 16;
+}
+
 // NCHW fp32 (optionally a (B,T,C,H,W) time slice) -> NHWC E with channel padding (zeros).
 template <typename E>
 __global__ void pack_nhwc_kernel(const float* __restrict__ src, E* __restrict__ dst, int B, int C, int H, int W,

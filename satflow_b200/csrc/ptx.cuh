@@ -194,6 +194,53 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return fmaf(2.0f, __fdividef(1.0f, 1.0f + exp2f(-2.8853900817779268f * x)), -1.0f);
 }
 
+// Raw MUFU wrappers (flush-to-zero: callers clamp their arguments, so no denormal fix-up code is emitted).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
+
+// The four gates of one hidden channel with ONE reciprocal: with d_x = 1 + e^{-z_x} (d_g = 1 + e^{-2 z_g}),
+// r = 1 / (d_i d_f d_o d_g) gives every 1/d_x by multiplications on the FMA pipe.  Arguments are clamped
+// to +-20 so the product stays below e^80 (fp32 max is e^88.7); sigmoid(-20) = 2e-9 is below fp32 noise
+// for every use downstream.  4 EX2 + 1 RCP instead of 4 EX2 + 4 RCP.
+__device__ __forceinline__ void lstm_gates_shared_rcp(float zi, float zf, float zo, float zg, float& gi, float& gf,
+                                                      float& go, float& gg) {
+  constexpr float kL2e = 1.4426950408889634f;
+  const float di = 1.f + ex2_ftz(clampf(-zi, 20.f) * kL2e);
+  const float df = 1.f + ex2_ftz(clampf(-zf, 20.f) * kL2e);
+  const float dO = 1.f + ex2_ftz(clampf(-zo, 20.f) * kL2e);
+  const float dg = 1.f + ex2_ftz(clampf(-2.f * zg, 20.f) * kL2e);
+  const float a = di * df, b = dO * dg;
+  const float r = rcp_ftz(a * b);
+  const float ra = r * b, rb = r * a;  // 1/(di df), 1/(do dg)
+  gi = ra * df;
+  gf = ra * di;
+  go = rb * dg;
+  gg = fmaf(2.f, rb * dO, -1.f);
+}
+// tanh of two values with one reciprocal (arguments clamped to +-40: product below e^80).
+__device__ __forceinline__ void tanh_pair_shared_rcp(float xa, float xb, float& ta, float& tb) {
+  constexpr float kL2e = 1.4426950408889634f;
+  const float da = 1.f + ex2_ftz(clampf(-2.f * xa, 40.f) * kL2e);
+  const float db = 1.f + ex2_ftz(clampf(-2.f * xb, 40.f) * kL2e);
+  const float r = rcp_ftz(da * db);
+  ta = fmaf(2.f, r * db, -1.f);
+  tb = fmaf(2.f, r * da, -1.f);
+}
+
 template <typename E>
 struct Elem;
 template <>

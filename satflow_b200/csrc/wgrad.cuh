@@ -123,8 +123,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // M = 128 (two 64-channel MN groups, LBO apart), N = 64, both operands MN-major.
-      const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 64, 1, 1);
+      // M = 128 (two 64-channel MN groups, LBO apart); both operands MN-major.  Up to four adjacent
+      // 64-column blocks (LBO apart) form ONE N = 256 instruction, so A is read from shared memory
+      // once per four blocks instead of once per block (N = 64 MMAs are smem-read bound).
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -132,7 +133,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tcgen05_fence_after();
         const uint32_t base = smem_u32(smem + stage * stage_bytes);
         const uint64_t adesc = make_smem_desc_sw128(base, kBoxBytes, 1024);
-        for (int j = 0; j < nblk; ++j) {
+        for (int j = 0; j < nblk; j += 4) {
+          const int nb4 = min(4, nblk - j);
+          const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 64 * nb4, 1, 1);
           const uint64_t bdesc = make_smem_desc_sw128(base + (2 + j) * kBoxBytes, kBoxBytes, 1024);
 #pragma unroll
           for (int k = 0; k < kWgTileP / 16; ++k) {

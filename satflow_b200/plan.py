@@ -124,10 +124,17 @@ class RolloutPlan:
                 )
             )
 
-    def profile_cell_step(self, cell: int, step: int) -> None:
-        """Re-launch the fused cell-step kernel of (cell, step) (measurement hook, include/clstm.h)."""
+    KERNELS = {"cell_fwd": 0, "gate_grad": 1, "dgrad": 2, "wgrad": 3}
+
+    def profile_kernel(self, kind: str, cell: int, step: int) -> None:
+        """Re-launch one kernel of (cell, step) (measurement hook, include/clstm.h clstm_plan_profile_kernel)."""
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().clstm_plan_profile_cell_step(self._h, cell, step, _stream_ptr(self.device)))
+            _lib.check(
+                _lib.lib().clstm_plan_profile_kernel(self._h, self.KERNELS[kind], cell, step, _stream_ptr(self.device))
+            )
+
+    def profile_cell_step(self, cell: int, step: int) -> None:
+        self.profile_kernel("cell_fwd", cell, step)
 
     def read_state(self, cell: int, step: int):
         c = self.cfg
