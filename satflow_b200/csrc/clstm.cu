@@ -19,6 +19,7 @@
 
 #include "../../include/clstm.h"
 #include "convgemm.cuh"
+#include "convgemm2.cuh"
 #include "pointwise.cuh"
 #include "selftest.cuh"
 #include "wgrad.cuh"
@@ -123,6 +124,30 @@ int make_map_act(CUtensorMap* m, int dtype, const void* ptr, int C, int W, int H
   return 0;
 }
 
+// Epilogue tensor maps: [N][H][W][C] tensors accessed in [boxH x boxW pixel] x 16-channel boxes.  fp32 tensors
+// (c states, dgrad outputs) use 64-byte rows + SWIZZLE_64B, 16-bit tensors (h, gates) 32-byte rows + SWIZZLE_32B,
+// matching the conflict-free staging layout of the convgemm epilogue.  TMA stores clip out-of-bounds pixels.
+int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, int C, int W, int H, long long N,
+                 int boxW, int boxH) {
+  EncodeTiledFn enc;
+  RC_TRY(get_encode(&enc));
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)W * C * elem_bytes,
+                           (cuuint64_t)H * W * C * elem_bytes};
+  cuuint32_t box[4] = {16, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (dtype16 == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(m, dt, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(epilogue C=%d W=%d H=%d N=%lld elem %d) -> %d", C, W, H, N,
+                elem_bytes, (int)r);
+  return 0;
+}
+
 // Packed weight matrix [rows][K] (K-major); box = 64 k x boxRows rows.
 int make_map_w(CUtensorMap* m, int dtype, const void* ptr, int K, int rows, int boxRows) {
   EncodeTiledFn enc;
@@ -182,7 +207,8 @@ struct Ctx {
   void* dz = nullptr;      // E [npix][4HP]
   float* scale = nullptr;  // device {S, 1/S}
   unsigned int* amax = nullptr;
-  CUtensorMap m_dz128, m_dz64;
+  CUtensorMap m_dz128, m_dz64, m_dzhalo;
+  bool pair_ok = false;  // geometry allows the CTA-pair halo kernel (one-row 128-pixel tiles)
 };
 
 struct CellState {
@@ -210,7 +236,8 @@ struct CellState {
   float* dc = nullptr;      // fp32 [npix][HP]
   float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
-  CUtensorMap m_h128, m_h64, m_wp, m_wd;
+  CUtensorMap m_h128, m_h64, m_hhalo, m_wp, m_wd, m_wp_half, m_wd_half;
+  CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
 };
@@ -219,6 +246,7 @@ struct CellState {
 struct InputRef {
   const CUtensorMap* map128 = nullptr;
   const CUtensorMap* map64 = nullptr;
+  const CUtensorMap* maphalo = nullptr;  // one-row halo boxes (pair kernel); == map128 for direct inputs
   int b_off = 0;  // image offset (slot * B)
 };
 
@@ -293,23 +321,44 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
   RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256));
   if (ctx.training) RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
+  RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
+                      g.BH));
+  RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
+  if (ctx.training) {
+    RC_TRY(make_map_epi(&cs.m_g16, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
+                        g.BW, g.BH));
+    RC_TRY(make_map_epi(&cs.m_dh16, 4, ctx.dtype, cs.dh_own, ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
+    if (cs.with_x) RC_TRY(make_map_epi(&cs.m_dx16, 4, ctx.dtype, cs.dxb, cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
+  }
+  if (ctx.pair_ok) {
+    RC_TRY(make_map_act(&cs.m_hhalo, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 128 + cs.g.kw - 1, 1));
+    RC_TRY(make_map_w(&cs.m_wp_half, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
+    if (ctx.training) RC_TRY(make_map_w(&cs.m_wd_half, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / 2));
+  }
   return 0;
 }
 
 // --------------------------------------------------------------------------- launch helpers
 template <typename E, int EPI>
 int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                    ConvGemmParams p, const Geo& g, long long images, cudaStream_t st) {
+                    ConvGemmParams p, const Geo& g, long long images, cudaStream_t st,
+                    const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr) {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  // staged epilogue: 0 = direct per-thread stores, 1 = TMA stores, 2 = cooperative coalesced stores (EPI_LSTM)
+  p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? env_int("CLSTM_STAGED", EPI == EPI_LSTM ? 2 : 1) : 0;
+  if (EPI == EPI_STORE && p.staged == 2) p.staged = 1;
+  const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;
-  const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles));
+  const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));
   int stages = (dev.smem_optin - fixed) / stage_bytes;
+  const int max_stages = env_int("CLSTM_STAGES", kMaxStages);
+  if (stages > max_stages) stages = max_stages;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(CLSTM_EINVAL, "convgemm: not enough shared memory for n_tile=%d", p.n_tile);
   p.stages = stages;
-  const size_t smem = convgemm_smem_bytes(stages, p.n_tile, p.n_tiles);
+  const size_t smem = convgemm_smem_bytes(stages, p.n_tile, p.n_tiles, stg_half);
   static bool attr_set = false;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(convgemm_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -318,8 +367,52 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   }
   const int total = p.num_m_tiles * p.n_tiles;
   const int grid = total < dev.sms ? total : dev.sms;
-  convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, p);
+  convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0 ? *x0 : b, x1 ? *x1 : b, x2 ? *x2 : b, p);
   return after_launch("convgemm_kernel");
+}
+
+// CTA-pair, halo-stationary variant (convgemm2.cuh).  `a0/a1` must be one-row halo maps (box 128 + kw - 1)
+// for conv segments and plain 128-pixel maps for direct segments; `b` a half-tile weight map.
+template <typename E, int EPI>
+int launch_pairgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                    ConvGemmParams p, const Geo& g, long long images, cudaStream_t st, bool* used) {
+  *used = false;
+  if (g.BW != 128 || g.BH != 1 || !env_int("CLSTM_PAIR", 0)) return 0;
+  PairGemmParams pp;
+  memset(&pp, 0, sizeof(pp));
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  int slot = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    pp.halo_w[s] = 128 + p.seg[s].kw - 1;
+    pp.pitch[s] = round_up(pp.halo_w[s], 8);
+    const int bytes = p.seg[s].kh * pp.pitch[s] * 128;
+    if (bytes > slot) slot = bytes;
+  }
+  pp.a_slot_bytes = slot;
+  pp.a_stages = env_int("CLSTM_PAIR_ASTAGES", 2);
+  if (pp.a_stages < 1 || pp.a_stages > kPairMaxAStages) pp.a_stages = 2;
+  const int b_stage = (p.n_tile / 2) * 128;
+  const long long fixed = static_cast<long long>(pairgemm_smem_bytes(pp.a_stages, slot, 0, p.n_tile, p.n_tiles));
+  long long bs = (dev.smem_optin - fixed) / b_stage;
+  if (bs > kPairMaxBStages) bs = kPairMaxBStages;
+  if (bs < 2) return 0;  // does not fit (large kernels): caller falls back to the per-tap kernel
+  pp.b_stages = static_cast<int>(bs);
+  pp.g = p;
+  const size_t smem = pairgemm_smem_bytes(pp.a_stages, slot, pp.b_stages, p.n_tile, p.n_tiles);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(pairgemm_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dev.smem_optin));
+    attr_set = true;
+  }
+  const int units = ((p.num_m_tiles + 1) / 2) * p.n_tiles;
+  int clusters = dev.sms / 2;
+  if (clusters > units) clusters = units;
+  pairgemm_kernel<E, EPI><<<2 * clusters, kGemmThreads, smem, st>>>(a0, a1, b, pp);
+  *used = true;
+  return after_launch("pairgemm_kernel");
 }
 
 template <typename E>
@@ -379,7 +472,8 @@ int pack_cell(const Ctx& ctx, CellState& cs, const float* w, const float* bias, 
 // writes h slot `sn`, c_next (and the gates when training).
 template <typename E>
 int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int sn, const float* c_prev,
-                      float* c_next, void* gates, cudaStream_t st) {
+                      float* c_next, void* gates, cudaStream_t st, int cprev_slot = -1, int cnext_slot = -1,
+                      int gates_step = -1) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   const CellGeom& g = cs.g;
@@ -397,7 +491,22 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.h_next = static_cast<E*>(cs.h) + static_cast<size_t>(sn) * cs.h_slot_elems(ctx.geo);
   p.gates = gates;
   p.ldc = ctx.HP;
-  p.act_mode = env_int("CLSTM_ACT_MODE", 0);
+  p.act_mode = env_int("CLSTM_ACT_MODE", 3);
+  p.skip_mask = env_int("CLSTM_SKIP", 0);
+  if (ctx.pair_ok) {
+    bool used = false;
+    RC_TRY((launch_pairgemm<E, EPI_LSTM>(ctx.dev, *in.maphalo, cs.m_hhalo, cs.m_wp_half, p, ctx.geo, ctx.geo.B, st,
+                                         &used)));
+    if (used) return 0;
+  }
+  if (cnext_slot >= 0) {  // staged epilogue: image offsets into the c / h / gates stacks
+    p.cprev_boff = (c_prev != nullptr && cprev_slot >= 0) ? cprev_slot * ctx.geo.B : -1;
+    p.cnext_boff = cnext_slot * ctx.geo.B;
+    p.hnext_boff = sn * ctx.geo.B;
+    p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
+    return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
+                                        &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16);
+  }
   return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
 }
 
@@ -429,7 +538,14 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
   p.ld0 = g.CIP;
   p.ld1 = ctx.HP;
   p.out_scale = 1.f;
-  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, ctx.geo, ctx.geo.B, st);
+  if (ctx.pair_ok) {
+    bool used = false;
+    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, ctx.m_dzhalo, ctx.m_dzhalo, cs.m_wd_half, p, ctx.geo, ctx.geo.B, st,
+                                          &used)));
+    if (used) return 0;
+  }
+  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, ctx.geo, ctx.geo.B, st,
+                                       cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16);
 }
 
 template <typename E>
@@ -519,7 +635,7 @@ struct clstm_plan {
   float* hpart = nullptr;     // fp32 [splits][128*(KG/128)][HP]
   float* hbpart = nullptr;    // fp32 [C_out][kHeadBiasChunks]
   int head_splits = 0, head_group = 0, n_tile_hd = 0;
-  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd;
+  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16;
 };
 
 namespace {
@@ -558,15 +674,15 @@ InputRef plan_input(clstm_plan* p, int k, int t) {
   const int B = p->cfg.batch;
   const int L = p->L;
   if (k == 0) {
-    in.map128 = &p->m_xcol128, in.map64 = &p->m_xcol64, in.b_off = t * B;  // x[:, t]  (:177)
+    in.map128 = &p->m_xcol128, in.map64 = &p->m_xcol64, in.maphalo = &p->m_xcol128, in.b_off = t * B;  // x[:, t] (:177)
   } else if (k == L) {
     // decoder_1 input: encoder_vector (:185, :189) = last encoder h at t == 0, else last decoder h (:195)
     const CellState& src = (t == 0) ? p->cells[L - 1] : p->cells[p->ncell - 1];
     const int s = (t == 0) ? hslot(src, p->cfg.t_in) : hslot(src, t);
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.b_off = s * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.maphalo = &src.m_hhalo, in.b_off = s * B;
   } else {
     const CellState& src = p->cells[k - 1];  // the layer below, already stepped to t + 1 (:180, :192)
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.b_off = hslot(src, t + 1) * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.maphalo = &src.m_hhalo, in.b_off = hslot(src, t + 1) * B;
   }
   return in;
 }
@@ -615,7 +731,8 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
     float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
     void* gates = c.training ? static_cast<void*>(static_cast<E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP)
                              : nullptr;
-    return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st);
+    return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st, cslot(cs, t),
+                                cslot(cs, t + 1), t);
   };
   for (int t = 0; t < c.t_in; ++t)  // conv_lstm.py:176-183
     for (int l = 0; l < L; ++l) RC_TRY(step(l, t));
@@ -712,7 +829,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       hp.out0 = p->dstack, hp.out1 = p->dstack;
       hp.split_col = HP, hp.ld0 = HP, hp.ld1 = HP;
       hp.out_scale = 1.f;
-      RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st)));
+      RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st,
+                                            &p->m_dstack16, &p->m_dstack16, &p->m_dstack16)));
     }
     {
       WgradParams wp;
@@ -780,7 +898,7 @@ struct clstm_cell_plan {
   size_t ws_bytes = 0;
   bool bound = false, forward_done = false;
   void* xin = nullptr;  // E [npix][CIP]
-  CUtensorMap m_x128, m_x64;
+  CUtensorMap m_x128, m_x64, m_xhalo;
 };
 
 namespace {
@@ -817,8 +935,8 @@ int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, con
   pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(c_cur, cs.c, geo.B, p->hid, geo.H, geo.W, HP, nullptr);
   RC_TRY(after_launch("pack_nhwc_f32_kernel"));
   InputRef in;
-  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
-  RC_TRY(cell_forward_step<E>(ctx, cs, in, 0, 1, cs.c, cs.c + npix * HP, cs.gates, st));
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.maphalo = &p->m_xhalo, in.b_off = 0;
+  RC_TRY(cell_forward_step<E>(ctx, cs, in, 0, 1, cs.c, cs.c + npix * HP, cs.gates, st, 0, 1, 0));
   if (h_next) {
     unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(static_cast<const E*>(cs.h) + npix * HP, h_next, geo.B, p->hid,
                                                        geo.H, geo.W, HP, nullptr, 0);
@@ -870,7 +988,7 @@ int cellplan_backward(clstm_cell_plan* p, const float* dh_next, const float* dc_
   }
   cs.bwd_started = false;
   InputRef in;
-  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.maphalo = &p->m_xhalo, in.b_off = 0;
   RC_TRY(cell_backward_step<E>(ctx, cs, in, 0, cs.gates, cs.c, cs.c + npix * HP, dh_src, nullptr, nullptr, st));
   RC_TRY(cell_finalize(ctx, cs, dweight, dbias, 0, st));
   if (dx) {
@@ -934,6 +1052,7 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
   DeviceInfo dev;
   if (get_device(&dev) == 0) ctx.dev = dev;
   ctx.geo = make_geo(cfg->batch, cfg->height, cfg->width);
+  ctx.pair_ok = (ctx.geo.BW == 128 && ctx.geo.BH == 1);
   ctx.dtype = cfg->dtype;
   ctx.HP = pad_hidden(cfg->hidden);
   ctx.training = cfg->training;
@@ -1002,9 +1121,12 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   if (c.training) {
     RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
+    if (ctx.pair_ok)
+      RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
     RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
     RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
+    RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
   p->bound = true;
   p->weights_set = false;
@@ -1083,7 +1205,9 @@ int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, voi
   if (p->cfg.training) gates = static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(step) * npix * 4 * HP * 2;
   switch (kind) {
     case CLSTM_KERNEL_CELL_FWD: {
-#define CALL_(E) cell_forward_step<E>(p->ctx, cs, in, hslot(cs, step), hslot(cs, step + 1), c_prev, c_next, gates, st)
+#define CALL_(E)                                                                                              \
+  cell_forward_step<E>(p->ctx, cs, in, hslot(cs, step), hslot(cs, step + 1), c_prev, c_next, gates, st,               \
+                       cslot(cs, step), cslot(cs, step + 1), step)
       return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
     }
@@ -1119,6 +1243,7 @@ int clstm_cell_plan_create(int batch, int height, int width, int in_channels, in
   DeviceInfo dev;
   if (get_device(&dev) == 0) ctx.dev = dev;
   ctx.geo = make_geo(batch, height, width);
+  ctx.pair_ok = (ctx.geo.BW == 128 && ctx.geo.BH == 1);
   ctx.dtype = dtype;
   ctx.HP = pad_hidden(hidden);
   ctx.training = 1;
@@ -1156,6 +1281,10 @@ int clstm_cell_plan_bind(clstm_cell_plan_t* p, void* workspace, size_t bytes, vo
   RC_TRY(make_map_act(&p->m_x64, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, g.BW2, g.BH2));
   RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
   RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW2, g.BH2));
+  if (ctx.pair_ok) {
+    RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
+    RC_TRY(make_map_act(&p->m_xhalo, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
+  }
   p->bound = true;
   p->forward_done = false;
   return 0;

@@ -29,6 +29,18 @@ constexpr int kABytes = kTileM * 128;
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 384;
 constexpr int kTmemCols = 512;
+// Epilogue staging, per half (4 warps = 128 pixel rows x one 16-channel group):
+//   [c_prev 8 KB][c 8 KB][h 4 KB][gates 4 x 4 KB]   (EPI_STORE uses the c slot only)
+constexpr int kStgCprev = 0, kStgC = 8192, kStgH = 16384, kStgG = 20480;
+constexpr int kStgHalfLstm = 36864;   // EPI_LSTM
+constexpr int kStgHalfStore = 8192;   // EPI_STORE: one fp32 [128 x 16] group
+__host__ __device__ constexpr int stg_half_bytes(int epi) {
+  return epi == 0 /*EPI_LSTM*/ ? kStgHalfLstm : (epi == 1 /*EPI_STORE*/ ? kStgHalfStore : 0);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 struct ConvSeg {
   int chunks;  // 64-channel chunks of this segment's activation tensor
@@ -54,6 +66,10 @@ struct ConvGemmParams {
   void* h_next;         // E    [pixel][ldc]
   void* gates;          // E    [pixel][4*ldc] ([i|f|o|g] blocks of ldc) or nullptr
   int ldc;              // padded hidden channels (multiple of 64)
+  // staged epilogue (TMA stores / c_prev TMA load): image offsets into the epilogue tensor maps
+  int staged;           // 1: outputs go through shared memory + TMA (tmX0..tmX2), 0: direct per-thread stores
+  int cprev_boff, cnext_boff, hnext_boff, gates_boff;
+  int skip_mask;        // experiment: bit 0 skip c store, bit 1 skip h store, bit 2 skip gate stores
   int act_mode;         // 0: one reciprocal per activation; 1: tanh.approx (experiment); 2: no MUFU (experiment);
                         // 3: shared reciprocals (default)
   // ---- EPI_STORE
@@ -67,19 +83,176 @@ struct ConvGemmParams {
   int c_out, t_out, b_img;
 };
 
+// Epilogue of one 128-pixel x n_tile accumulator tile for the calling warp: TMEM -> registers -> fused
+// pointwise math -> global.  `taddr` already carries the warp's lane quadrant and the accumulator's column
+// base; `half` selects which half of the column groups this warp handles (two warps share a quadrant).
+template <typename E, int EPI>
+__device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, const float* bias_s, uint32_t taddr,
+                                                       int nt, int b, int hy, int wx, bool valid, size_t pix,
+                                                       int half) {
+  if constexpr (EPI == EPI_LSTM) {
+    // N tile = [i(64) | f(64) | o(64) | g(64)] for hidden channels nt*64 .. nt*64+63
+    const float* bs = bias_s + nt * 256;
+#pragma unroll 1
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const int j0 = half * 32 + g2 * 16;
+      uint32_t vi[16], vf[16], vo[16], vg[16];
+      tmem_ld16(taddr + 0 + j0, vi);
+      tmem_ld16(taddr + 64 + j0, vf);
+      tmem_ld16(taddr + 128 + j0, vo);
+      tmem_ld16(taddr + 192 + j0, vg);
+      tmem_ld_wait();
+      if (valid) {
+        const size_t off = pix * p.ldc + nt * 64 + j0;
+        float cp[16];
+        if (p.c_prev != nullptr && p.act_mode != 4) {
+          const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4 t = __ldg(src + e);
+            cp[4 * e + 0] = t.x, cp[4 * e + 1] = t.y, cp[4 * e + 2] = t.z, cp[4 * e + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cp[e] = 0.f;
+        }
+        float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
+        if (p.act_mode == 3) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
+                                  __uint_as_float(vo[e]) + bs[128 + j0 + e],
+                                  __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float ta, tb;
+            tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
+            hn[e] = go[e] * ta;
+            hn[e + 1] = go[e + 1] * tb;
+          }
+        } else if (p.act_mode == 1) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            gi[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vi[e]) + bs[0 + j0 + e])), 0.5f);
+            gf[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vf[e]) + bs[64 + j0 + e])), 0.5f);
+            go[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vo[e]) + bs[128 + j0 + e])), 0.5f);
+            gg[e] = tanh_mufu(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+            hn[e] = go[e] * tanh_mufu(cn[e]);
+          }
+        } else if (p.act_mode == 2) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            gi[e] = __uint_as_float(vi[e]) + bs[0 + j0 + e];
+            gf[e] = __uint_as_float(vf[e]) + bs[64 + j0 + e];
+            go[e] = __uint_as_float(vo[e]) + bs[128 + j0 + e];
+            gg[e] = __uint_as_float(vg[e]) + bs[192 + j0 + e];
+            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+            hn[e] = go[e] * cn[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
+            gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
+            go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
+            gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+            hn[e] = go[e] * fast_tanh(cn[e]);
+          }
+        }
+        if (p.act_mode == 4) {  // experiment: no epilogue stores (one predicated-off store keeps the math alive)
+          float acc_x = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc_x += cn[e] + hn[e] + gi[e] + gf[e] + go[e] + gg[e];
+          if (acc_x == 1.2345e30f) p.c_next[off] = acc_x;
+          continue;
+        }
+        float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          cdst[e] = make_float4(cn[4 * e], cn[4 * e + 1], cn[4 * e + 2], cn[4 * e + 3]);
+        uint4* hdst = reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + off);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          hdst[e] = make_uint4(Elem<E>::pack2(hn[8 * e + 0], hn[8 * e + 1]), Elem<E>::pack2(hn[8 * e + 2], hn[8 * e + 3]),
+                               Elem<E>::pack2(hn[8 * e + 4], hn[8 * e + 5]), Elem<E>::pack2(hn[8 * e + 6], hn[8 * e + 7]));
+        if (p.gates != nullptr) {
+          E* gbase = reinterpret_cast<E*>(p.gates) + pix * (4 * static_cast<size_t>(p.ldc)) + nt * 64 + j0;
+          const float* gsrc[4] = {gi, gf, go, gg};
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt) {
+            uint4* gd = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(gt) * p.ldc);
+            const float* gv = gsrc[gt];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              gd[e] = make_uint4(Elem<E>::pack2(gv[8 * e + 0], gv[8 * e + 1]), Elem<E>::pack2(gv[8 * e + 2], gv[8 * e + 3]),
+                                 Elem<E>::pack2(gv[8 * e + 4], gv[8 * e + 5]), Elem<E>::pack2(gv[8 * e + 6], gv[8 * e + 7]));
+          }
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_STORE) {
+    const int groups = p.n_tile / 16;
+#pragma unroll 1
+    for (int g = half; g < groups; g += 2) {
+      uint32_t v[16];
+      tmem_ld16(taddr + g * 16, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int col = nt * p.n_tile + g * 16;
+        float* dst = (col < p.split_col) ? (p.out0 + pix * p.ld0 + col)
+                                         : (p.out1 + pix * p.ld1 + (col - p.split_col));
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          d4[e] = make_float4(__uint_as_float(v[4 * e]) * p.out_scale, __uint_as_float(v[4 * e + 1]) * p.out_scale,
+                              __uint_as_float(v[4 * e + 2]) * p.out_scale, __uint_as_float(v[4 * e + 3]) * p.out_scale);
+      }
+    }
+  } else {  // EPI_HEAD
+    const int groups = p.n_tile / 16;
+    const int t = b / p.b_img, bi = b % p.b_img;
+    const size_t plane = static_cast<size_t>(p.H) * p.W;
+#pragma unroll 1
+    for (int g = half; g < groups; g += 2) {
+      uint32_t v[16];
+      tmem_ld16(taddr + g * 16, v);
+      tmem_ld_wait();
+      if (valid) {
+        float* ybase = p.y + ((static_cast<size_t>(bi) * p.c_out) * p.t_out + t) * plane +
+                       static_cast<size_t>(hy) * p.W + wx;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int co = nt * p.n_tile + g * 16 + e;
+          if (co < p.c_out)
+            ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(__uint_as_float(v[e]) + bias_s[co]);
+        }
+      }
+    }
+  }
+}
+
 template <typename E, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX0,
+                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kABytes + p.n_tile * 128;
-  uint8_t* tail = smem + p.stages * stage_bytes;
+  uint8_t* smem_stg = smem + p.stages * stage_bytes;  // epilogue staging (1024-aligned: stage_bytes is)
+  const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
+  uint8_t* tail = smem_stg + 2 * stg_half;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* cprev_full = tmem_empty + 2;  // [2], one per epilogue half
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cprev_full + 4);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // n_tiles * n_tile floats
 
   const int warp = threadIdx.x >> 5;
@@ -99,6 +272,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
+      mbar_init(&cprev_full[a], 1);
     }
     fence_barrier_init();
   }
@@ -185,47 +359,87 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int hl = r / p.BW, wl = r % p.BW;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int b = mt / (p.tiles_w * p.tiles_h);
-      const int hy = th * p.BH + hl, wx = tw * p.BW + wl;
-      const bool valid = (hy < p.H) && (wx < p.W);
-      const size_t pix = (static_cast<size_t>(b) * p.H + hy) * p.W + wx;
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-
+    bool staged_path = false;
+    if constexpr (EPI == EPI_LSTM || EPI == EPI_STORE) staged_path = (p.staged != 0);
+    if (staged_path) {
+      // ---- staged epilogue: registers -> swizzled shared memory -> TMA stores (and c_prev by TMA load).
+      // The four warps of a half own one [128 px x 16 ch] group at a time; two named-barrier syncs per group.
+      uint8_t* stg = smem_stg + half * stg_half;
+      const bool issuer = (q == 0) && (lane == 0);
+      const int bar_id = 1 + half;
+      const uint32_t x64 = (static_cast<uint32_t>(r) >> 1) & 3u;  // SWIZZLE_64B: 16-B chunk ^= row bits [1,2]
+      const uint32_t x32 = (static_cast<uint32_t>(r) >> 2) & 1u;  // SWIZZLE_32B: 16-B chunk ^= row bit 2
+      auto coords = [&](int tile, int& nt, int& w0, int& h0, int& b) {
+        const int mt = tile / p.n_tiles;
+        nt = tile % p.n_tiles;
+        w0 = (mt % p.tiles_w) * p.BW;
+        h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
+        b = mt / (p.tiles_w * p.tiles_h);
+      };
       if constexpr (EPI == EPI_LSTM) {
-        // N tile = [i(64) | f(64) | o(64) | g(64)] for hidden channels nt*64 .. nt*64+63
-        const float* bs = bias_s + nt * 256;
+        const bool has_cprev = p.cprev_boff >= 0 && p.act_mode != 6;
+        uint32_t cp_phase = 0;
+        if (issuer && has_cprev && static_cast<int>(blockIdx.x) < total_tiles) {
+          int nt, w0, h0, b;
+          coords(blockIdx.x, nt, w0, h0, b);
+          mbar_expect_tx(&cprev_full[half], 8192);
+          tma_load_4d(stg + kStgCprev, &tmX0, &cprev_full[half], nt * 64 + half * 32, w0, h0, b + p.cprev_boff);
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int nt, w0, h0, b;
+          coords(tile, nt, w0, h0, b);
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+          const float* bs = bias_s + nt * 256;
 #pragma unroll 1
-        for (int g2 = 0; g2 < 2; ++g2) {
-          const int j0 = half * 32 + g2 * 16;
-          uint32_t vi[16], vf[16], vo[16], vg[16];
-          tmem_ld16(taddr + 0 + j0, vi);
-          tmem_ld16(taddr + 64 + j0, vf);
-          tmem_ld16(taddr + 128 + j0, vo);
-          tmem_ld16(taddr + 192 + j0, vg);
-          tmem_ld_wait();
-          if (valid) {
-            const size_t off = pix * p.ldc + nt * 64 + j0;
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int j0 = half * 32 + g2 * 16;
+            uint32_t vi[16], vf[16], vo[16], vg[16];
+            tmem_ld16(taddr + 0 + j0, vi);
+            tmem_ld16(taddr + 64 + j0, vf);
+            tmem_ld16(taddr + 128 + j0, vo);
+            tmem_ld16(taddr + 192 + j0, vg);
             float cp[16];
-            if (p.c_prev != nullptr) {
-              const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
+            if (has_cprev) {
+              mbar_wait(&cprev_full[half], cp_phase);
+              cp_phase ^= 1;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float4 t = __ldg(src + e);
-                cp[4 * e + 0] = t.x, cp[4 * e + 1] = t.y, cp[4 * e + 2] = t.z, cp[4 * e + 3] = t.w;
+              for (uint32_t j = 0; j < 4; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(stg + kStgCprev + r * 64 + ((j ^ x64) << 4));
+                cp[4 * j + 0] = t.x, cp[4 * j + 1] = t.y, cp[4 * j + 2] = t.z, cp[4 * j + 3] = t.w;
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) cp[e] = 0.f;
             }
+            if (issuer) tma_store_wait_read();  // the previous group's stores have finished reading the staging
+            named_bar_sync(bar_id, 128);        // staging is free; everyone has consumed c_prev
+            if (issuer && has_cprev) {          // prefetch the next group's c_prev behind this group's math
+              int tn = tile, ntn = nt, w0n = w0, h0n = h0, bn = b, j0n = j0 + 16;
+              if (g2 == 1) {
+                tn = tile + gridDim.x;
+                j0n = half * 32;
+                if (tn < total_tiles) coords(tn, ntn, w0n, h0n, bn);
+              }
+              if (tn < total_tiles) {
+                mbar_expect_tx(&cprev_full[half], 8192);
+                tma_load_4d(stg + kStgCprev, &tmX0, &cprev_full[half], ntn * 64 + j0n, w0n, h0n, bn + p.cprev_boff);
+              }
+            }
+            tmem_ld_wait();
             float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
-            if (p.act_mode == 3) {
+            if (p.act_mode == 0) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
+                gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
+                go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
+                gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
+                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+                hn[e] = go[e] * fast_tanh(cn[e]);
+              }
+            } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
@@ -240,105 +454,151 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 hn[e] = go[e] * ta;
                 hn[e + 1] = go[e + 1] * tb;
               }
-            } else if (p.act_mode == 1) {
+            }
+            if (g2 == 1) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                gi[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vi[e]) + bs[0 + j0 + e])), 0.5f);
-                gf[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vf[e]) + bs[64 + j0 + e])), 0.5f);
-                go[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vo[e]) + bs[128 + j0 + e])), 0.5f);
-                gg[e] = tanh_mufu(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-                hn[e] = go[e] * tanh_mufu(cn[e]);
-              }
-            } else if (p.act_mode == 2) {
+            for (uint32_t j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + kStgC + r * 64 + ((j ^ x64) << 4)) =
+                  make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+            auto pack8 = [](const float* v) {
+              return make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]), Elem<E>::pack2(v[4], v[5]),
+                                Elem<E>::pack2(v[6], v[7]));
+            };
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                gi[e] = __uint_as_float(vi[e]) + bs[0 + j0 + e];
-                gf[e] = __uint_as_float(vf[e]) + bs[64 + j0 + e];
-                go[e] = __uint_as_float(vo[e]) + bs[128 + j0 + e];
-                gg[e] = __uint_as_float(vg[e]) + bs[192 + j0 + e];
-                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-                hn[e] = go[e] * cn[e];
-              }
-            } else {
+            for (uint32_t j = 0; j < 2; ++j)
+              *reinterpret_cast<uint4*>(stg + kStgH + r * 32 + ((j ^ x32) << 4)) = pack8(hn + 8 * j);
+            if (p.gates_boff >= 0) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
-                gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
-                go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
-                gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-                hn[e] = go[e] * fast_tanh(cn[e]);
+              for (uint32_t j = 0; j < 2; ++j) {
+                *reinterpret_cast<uint4*>(stg + kStgG + 0 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gi + 8 * j);
+                *reinterpret_cast<uint4*>(stg + kStgG + 1 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gf + 8 * j);
+                *reinterpret_cast<uint4*>(stg + kStgG + 2 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(go + 8 * j);
+                *reinterpret_cast<uint4*>(stg + kStgG + 3 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gg + 8 * j);
               }
             }
-            float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (p.staged == 2) {
+              // Cooperative coalesced stores: the half's 128 threads sweep the staged [128 px x 16 ch] group in
+              // 16-byte chunks, consecutive threads -> consecutive chunks of a pixel, then the next pixel.
+              // (TMA stores of these 32/64-byte rows were request-rate bound: DESIGN.md §4.)
+              const int chan = nt * 64 + j0;
+              const int lbw = 31 - __clz(p.BW);
+              auto pixel_of = [&](int px, size_t& gp) {
+                const int hy = h0 + (px >> lbw), wx = w0 + (px & (p.BW - 1));
+                gp = (static_cast<size_t>(b) * p.H + hy) * p.W + wx;
+                return hy < p.H && wx < p.W;
+              };
+              if (p.act_mode < 5) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              cdst[e] = make_float4(cn[4 * e], cn[4 * e + 1], cn[4 * e + 2], cn[4 * e + 3]);
-            uint4* hdst = reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + off);
+                for (int it = 0; it < 4; ++it) {  // c: 4 chunks per pixel
+                  const uint32_t idx = it * 128 + r, px = idx >> 2, ch = idx & 3;
+                  const float4 v = *reinterpret_cast<const float4*>(stg + kStgC + px * 64 + ((ch ^ ((px >> 1) & 3)) << 4));
+                  size_t gp;
+                  if (pixel_of(px, gp)) *reinterpret_cast<float4*>(p.c_next + gp * p.ldc + chan + ch * 4) = v;
+                }
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-              hdst[e] = make_uint4(Elem<E>::pack2(hn[8 * e + 0], hn[8 * e + 1]), Elem<E>::pack2(hn[8 * e + 2], hn[8 * e + 3]),
-                                   Elem<E>::pack2(hn[8 * e + 4], hn[8 * e + 5]), Elem<E>::pack2(hn[8 * e + 6], hn[8 * e + 7]));
-            if (p.gates != nullptr) {
-              E* gbase = reinterpret_cast<E*>(p.gates) + pix * (4 * static_cast<size_t>(p.ldc)) + nt * 64 + j0;
-              const float* gsrc[4] = {gi, gf, go, gg};
+                for (int it = 0; it < 2; ++it) {  // h: 2 chunks per pixel
+                  const uint32_t idx = it * 128 + r, px = idx >> 1, ch = idx & 1;
+                  const uint4 v = *reinterpret_cast<const uint4*>(stg + kStgH + px * 32 + ((ch ^ ((px >> 2) & 1)) << 4));
+                  size_t gp;
+                  if (pixel_of(px, gp))
+                    *reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + gp * p.ldc + chan + ch * 8) = v;
+                }
+                if (p.gates != nullptr) {
 #pragma unroll
-              for (int gt = 0; gt < 4; ++gt) {
-                uint4* gd = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(gt) * p.ldc);
-                const float* gv = gsrc[gt];
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                  gd[e] = make_uint4(Elem<E>::pack2(gv[8 * e + 0], gv[8 * e + 1]), Elem<E>::pack2(gv[8 * e + 2], gv[8 * e + 3]),
-                                     Elem<E>::pack2(gv[8 * e + 4], gv[8 * e + 5]), Elem<E>::pack2(gv[8 * e + 6], gv[8 * e + 7]));
+                  for (int it = 0; it < 8; ++it) {  // gates: 4 gates x 2 chunks per pixel
+                    const uint32_t idx = it * 128 + r, gt = idx >> 8, px = (idx & 255) >> 1, ch = idx & 1;
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + kStgG + gt * 4096 + px * 32 +
+                                                                    ((ch ^ ((px >> 2) & 1)) << 4));
+                    size_t gp;
+                    if (pixel_of(px, gp))
+                      *reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.gates) + gp * (4 * static_cast<size_t>(p.ldc)) +
+                                                gt * p.ldc + chan + ch * 8) = v;
+                  }
+                }
               }
+            } else if (issuer && p.act_mode < 5) {
+              const int chan = nt * 64 + j0;
+              if (!(p.skip_mask & 1)) tma_store_4d(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff);
+              if (!(p.skip_mask & 2)) tma_store_4d(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff);
+              if (p.gates_boff >= 0 && !(p.skip_mask & 4)) {
+#pragma unroll
+                for (int gt = 0; gt < 4; ++gt)
+                  tma_store_4d(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
+              }
+              tma_store_commit();
             }
           }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-      } else if constexpr (EPI == EPI_STORE) {
+      } else {  // EPI_STORE
         const int groups = p.n_tile / 16;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int nt, w0, h0, b;
+          coords(tile, nt, w0, h0, b);
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int g = half; g < groups; g += 2) {
-          uint32_t v[16];
-          tmem_ld16(taddr + g * 16, v);
-          tmem_ld_wait();
-          if (valid) {
-            const int col = nt * p.n_tile + g * 16;
-            float* dst = (col < p.split_col) ? (p.out0 + pix * p.ld0 + col)
-                                             : (p.out1 + pix * p.ld1 + (col - p.split_col));
-            float4* d4 = reinterpret_cast<float4*>(dst);
+          for (int g = half; g < groups; g += 2) {
+            uint32_t v[16];
+            tmem_ld16(taddr + g * 16, v);
+            if (issuer) tma_store_wait_read();
+            named_bar_sync(bar_id, 128);
+            tmem_ld_wait();
+            if (g + 2 >= groups) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              d4[e] = make_float4(__uint_as_float(v[4 * e]) * p.out_scale, __uint_as_float(v[4 * e + 1]) * p.out_scale,
-                                  __uint_as_float(v[4 * e + 2]) * p.out_scale, __uint_as_float(v[4 * e + 3]) * p.out_scale);
-          }
-        }
-      } else {  // EPI_HEAD
-        const int groups = p.n_tile / 16;
-        const int t = b / p.b_img, bi = b % p.b_img;
-        const size_t plane = static_cast<size_t>(p.H) * p.W;
-#pragma unroll 1
-        for (int g = half; g < groups; g += 2) {
-          uint32_t v[16];
-          tmem_ld16(taddr + g * 16, v);
-          tmem_ld_wait();
-          if (valid) {
-            float* ybase = p.y + ((static_cast<size_t>(bi) * p.c_out) * p.t_out + t) * plane +
-                           static_cast<size_t>(hy) * p.W + wx;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int co = nt * p.n_tile + g * 16 + e;
-              if (co < p.c_out)
-                ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(__uint_as_float(v[e]) + bias_s[co]);
+            for (uint32_t j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + r * 64 + ((j ^ x64) << 4)) =
+                  make_float4(__uint_as_float(v[4 * j]) * p.out_scale, __uint_as_float(v[4 * j + 1]) * p.out_scale,
+                              __uint_as_float(v[4 * j + 2]) * p.out_scale, __uint_as_float(v[4 * j + 3]) * p.out_scale);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (issuer) {
+              const int col = nt * p.n_tile + g * 16;
+              if (col < p.split_col)
+                tma_store_4d(&tmX0, stg, col, w0, h0, b);
+              else
+                tma_store_4d(&tmX1, stg, col - p.split_col, w0, h0, b);
+              tma_store_commit();
             }
           }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (issuer) tma_store_wait_all();  // outstanding bulk stores complete before the CTA retires
+    } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int b = mt / (p.tiles_w * p.tiles_h);
+        const int hy = th * p.BH + hl, wx = tw * p.BW + wl;
+        const bool valid = (hy < p.H) && (wx < p.W);
+        const size_t pix = (static_cast<size_t>(b) * p.H + hy) * p.W + wx;
+
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+
+        convgemm_epilogue_tile<E, EPI>(p, bias_s, taddr, nt, b, hy, wx, valid, pix, half);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   }
 
@@ -350,9 +610,9 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
 }
 
-inline size_t convgemm_smem_bytes(int stages, int n_tile, int n_tiles) {
-  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + (2 * kMaxStages + 4) * 8 + 16 +
-         static_cast<size_t>(n_tiles) * n_tile * 4 + 64;
+inline size_t convgemm_smem_bytes(int stages, int n_tile, int n_tiles, int stg_half = 0) {
+  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 2 * static_cast<size_t>(stg_half) +
+         (2 * kMaxStages + 8) * 8 + 16 + static_cast<size_t>(n_tiles) * n_tile * 4 + 64;
 }
 
 }  // namespace clstm

@@ -49,6 +49,12 @@ def main():
     stage("cell_fwdbwd_odd_fp16", lambda: G.cell_case(1, 5, 8, 7, 9, 3, 5, "fp16"))
     stage("cell_fwdbwd_h64_fp16", lambda: G.cell_case(1, 64, 64, 64, 64, 3, 3, "fp16"))
     stage("cell_fwdbwd_h128_k5_fp16", lambda: G.cell_case(1, 12, 128, 32, 32, 5, 5, "fp16"))
+    stage("cell_pair_W256", lambda: G.cell_case(1, 12, 64, 20, 256, 3, 3, "fp16"))
+    stage("cell_pair_W200_B2", lambda: G.cell_case(2, 64, 64, 6, 200, 3, 3, "fp16"))
+    stage("cell_pair_odd_tiles", lambda: G.cell_case(1, 12, 32, 3, 128, 3, 3, "fp16"))
+    stage("cell_pair_k5", lambda: G.cell_case(1, 12, 64, 9, 256, 5, 5, "fp16"))
+    stage("cell_pair_h128", lambda: G.cell_case(1, 12, 128, 5, 384, 3, 3, "fp16"))
+    stage("rollout_pair_W256", lambda: G.rollout_case(1, 3, 3, 12, 64, 12, 6, 256))
     stage("cell_golden_k3", lambda: G.cell_golden("cell_k3"))
     stage("cell_golden_k35", lambda: G.cell_golden("cell_k35"))
     stage("rollout_fwd_cfg1arch", lambda: G.rollout_case(2, 4, 4, 12, 32, 12, 64, 64, backward=False))
