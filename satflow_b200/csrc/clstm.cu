@@ -148,6 +148,14 @@ int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, i
   return 0;
 }
 
+// The weight tile of a stage is fetched as this many TMA boxes (issued by different lanes).
+inline int weight_boxes(int n_tile) {
+  // Measured: splitting the weight tile into 4 boxes slows the conv GEMMs (fwd 404 -> 427 us without epilogue,
+  // dgrad 673 -> 890 us); one box issued by its own lane (parallel with the A box) is best.
+  const int v = env_int("CLSTM_B_BOXES", 1);
+  return (v == 1 || v == 2 || v == 4) && n_tile % (8 * v) == 0 ? v : 1;
+}
+
 // Packed weight matrix [rows][K] (K-major); box = 64 k x boxRows rows.
 int make_map_w(CUtensorMap* m, int dtype, const void* ptr, int K, int rows, int boxRows) {
   EncodeTiledFn enc;
@@ -319,8 +327,9 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   const long long imgs = static_cast<long long>(cs.slots_h) * g.B;
   RC_TRY(make_map_act(&cs.m_h128, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
   RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
-  RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256));
-  if (ctx.training) RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
+  RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256 / weight_boxes(256)));
+  if (ctx.training)
+    RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / weight_boxes(cs.n_tile_d)));
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
                       g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
@@ -347,8 +356,9 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
   // staged epilogue: 0 = direct per-thread stores, 1 = TMA stores, 2 = cooperative coalesced stores (EPI_LSTM)
-  p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? env_int("CLSTM_STAGED", EPI == EPI_LSTM ? 2 : 1) : 0;
-  if (EPI == EPI_STORE && p.staged == 2) p.staged = 1;
+  p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? (env_int("CLSTM_STAGED", 1) ? 1 : 0) : 0;
+  p.b_boxes = weight_boxes(p.n_tile);
+  p.prod_serial = env_int("CLSTM_PROD_SERIAL", 0);
   const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));
@@ -384,14 +394,15 @@ int launch_pairgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
   int slot = 0;
+  pp.halo = env_int("CLSTM_PAIR_HALO", 1);
   for (int s = 0; s < p.nseg; ++s) {
     pp.halo_w[s] = 128 + p.seg[s].kw - 1;
     pp.pitch[s] = round_up(pp.halo_w[s], 8);
-    const int bytes = p.seg[s].kh * pp.pitch[s] * 128;
+    const int bytes = pp.halo ? p.seg[s].kh * pp.pitch[s] * 128 : kABytes;
     if (bytes > slot) slot = bytes;
   }
   pp.a_slot_bytes = slot;
-  pp.a_stages = env_int("CLSTM_PAIR_ASTAGES", 2);
+  pp.a_stages = env_int("CLSTM_PAIR_ASTAGES", pp.halo ? 2 : 4);
   if (pp.a_stages < 1 || pp.a_stages > kPairMaxAStages) pp.a_stages = 2;
   const int b_stage = (p.n_tile / 2) * 128;
   const long long fixed = static_cast<long long>(pairgemm_smem_bytes(pp.a_stages, slot, 0, p.n_tile, p.n_tiles));
@@ -426,6 +437,7 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(CLSTM_EINVAL, "wgrad: not enough shared memory");
   p.stages = stages;
+  p.dbg_no_tma = env_int("CLSTM_WG_NOTMA", 0);
   const size_t smem = wgrad_smem_bytes(stages, p.group_size);
   static bool attr_set = false;
   if (!attr_set) {
@@ -493,10 +505,12 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.ldc = ctx.HP;
   p.act_mode = env_int("CLSTM_ACT_MODE", 3);
   p.skip_mask = env_int("CLSTM_SKIP", 0);
+  p.lsu_mask = env_int("CLSTM_LSU", 0);
   if (ctx.pair_ok) {
     bool used = false;
-    RC_TRY((launch_pairgemm<E, EPI_LSTM>(ctx.dev, *in.maphalo, cs.m_hhalo, cs.m_wp_half, p, ctx.geo, ctx.geo.B, st,
-                                         &used)));
+    const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
+    RC_TRY((launch_pairgemm<E, EPI_LSTM>(ctx.dev, halo ? *in.maphalo : *in.map128, halo ? cs.m_hhalo : cs.m_h128,
+                                         cs.m_wp_half, p, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
   if (cnext_slot >= 0) {  // staged epilogue: image offsets into the c / h / gates stacks
@@ -540,8 +554,9 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
   p.out_scale = 1.f;
   if (ctx.pair_ok) {
     bool used = false;
-    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, ctx.m_dzhalo, ctx.m_dzhalo, cs.m_wd_half, p, ctx.geo, ctx.geo.B, st,
-                                          &used)));
+    const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
+    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, halo ? ctx.m_dzhalo : ctx.m_dz128, halo ? ctx.m_dzhalo : ctx.m_dz128,
+                                          cs.m_wd_half, p, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
   return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, ctx.geo, ctx.geo.B, st,
@@ -1117,7 +1132,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   const long long ximgs = static_cast<long long>(c.t_in) * c.batch;
   RC_TRY(make_map_act(&p->m_xcol128, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW, g.BH));
   RC_TRY(make_map_act(&p->m_xcol64, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW2, g.BH2));
-  RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT));
+  RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT / weight_boxes(p->NT)));
   if (c.training) {
     RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
@@ -1125,7 +1140,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
       RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
     RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
-    RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
+    RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd / weight_boxes(p->n_tile_hd)));
     RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
   p->bound = true;

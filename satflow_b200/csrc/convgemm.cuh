@@ -59,6 +59,8 @@ struct ConvGemmParams {
   int nseg;
   ConvSeg seg[2];
   int stages;
+  int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
+  int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
   // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
   const float* bias;  // [n_tiles * n_tile] in packed row order (all epilogues)
   const float* c_prev;  // fp32 [pixel][ldc] or nullptr (== zeros)
@@ -69,6 +71,7 @@ struct ConvGemmParams {
   // staged epilogue (TMA stores / c_prev TMA load): image offsets into the epilogue tensor maps
   int staged;           // 1: outputs go through shared memory + TMA (tmX0..tmX2), 0: direct per-thread stores
   int cprev_boff, cnext_boff, hnext_boff, gates_boff;
+  int lsu_mask;         // staged outputs written by cooperative st.global instead of TMA: bit 0 c, 1 h, 2 gates
   int skip_mask;        // experiment: bit 0 skip c store, bit 1 skip h store, bit 2 skip gate stores
   int act_mode;         // 0: one reciprocal per activation; 1: tanh.approx (experiment); 2: no MUFU (experiment);
                         // 3: shared reciprocals (default)
@@ -287,9 +290,13 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // One lane per box: lane 0 loads the A tile, lanes 1..b_boxes one slice of the weight tile each.  A single
+    // thread issuing every cp.async.bulk.tensor of a stage serialises on the issue latency (measured: the wgrad
+    // kernel went from 555 to 1250 TFLOP/s when its 8 boxes per stage were spread over 8 lanes).
+    if (lane <= (p.prod_serial ? 0 : p.b_boxes)) {
       int stage = 0;
       uint32_t phase = 0;
+      const int b_rows = p.n_tile / p.b_boxes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int tw = mt % p.tiles_w;
@@ -305,10 +312,19 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int ch = 0; ch < sg.chunks; ++ch, ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* a_dst = smem + stage * stage_bytes;
-                mbar_expect_tx(&full_bar[stage], stage_bytes);
-                tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
-                            h0 + dy - sg.kh / 2, b + sg.b_off);
-                tma_load_2d(a_dst + kABytes, &tmB, &full_bar[stage], kb * kBlockK, nt * p.n_tile);
+                if (lane == 0) {
+                  mbar_expect_tx(&full_bar[stage], stage_bytes);
+                  tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
+                              h0 + dy - sg.kh / 2, b + sg.b_off);
+                  if (p.prod_serial)
+                    for (int part = 0; part < p.b_boxes; ++part)
+                      tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
+                                  nt * p.n_tile + part * b_rows);
+                } else {
+                  const int part = lane - 1;
+                  tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
+                              nt * p.n_tile + part * b_rows);
+                }
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
@@ -413,8 +429,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 16; ++e) cp[e] = 0.f;
             }
-            if (issuer) tma_store_wait_read();  // the previous group's stores have finished reading the staging
-            named_bar_sync(bar_id, 128);        // staging is free; everyone has consumed c_prev
+            if (q == 0 && lane < 6) tma_store_wait_read();  // this lane's previous store has finished reading staging
+            named_bar_sync(bar_id, 128);                    // staging is free; everyone has consumed c_prev
             if (issuer && has_cprev) {          // prefetch the next group's c_prev behind this group's math
               int tn = tile, ntn = nt, w0n = w0, h0n = h0, bn = b, j0n = j0 + 16;
               if (g2 == 1) {
@@ -482,7 +498,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
-            if (p.staged == 2) {
+            if (p.lsu_mask) {
               // Cooperative coalesced stores: the half's 128 threads sweep the staged [128 px x 16 ch] group in
               // 16-byte chunks, consecutive threads -> consecutive chunks of a pixel, then the next pixel.
               // (TMA stores of these 32/64-byte rows were request-rate bound: DESIGN.md §4.)
@@ -494,6 +510,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 return hy < p.H && wx < p.W;
               };
               if (p.act_mode < 5) {
+                if (p.lsu_mask & 1) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {  // c: 4 chunks per pixel
                   const uint32_t idx = it * 128 + r, px = idx >> 2, ch = idx & 3;
@@ -501,6 +518,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   size_t gp;
                   if (pixel_of(px, gp)) *reinterpret_cast<float4*>(p.c_next + gp * p.ldc + chan + ch * 4) = v;
                 }
+                }
+                if (p.lsu_mask & 2) {
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {  // h: 2 chunks per pixel
                   const uint32_t idx = it * 128 + r, px = idx >> 1, ch = idx & 1;
@@ -509,7 +528,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   if (pixel_of(px, gp))
                     *reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + gp * p.ldc + chan + ch * 8) = v;
                 }
-                if (p.gates != nullptr) {
+                }
+                if (p.gates != nullptr && (p.lsu_mask & 4)) {
 #pragma unroll
                   for (int it = 0; it < 8; ++it) {  // gates: 4 gates x 2 chunks per pixel
                     const uint32_t idx = it * 128 + r, gt = idx >> 8, px = (idx & 255) >> 1, ch = idx & 1;
@@ -522,14 +542,18 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   }
                 }
               }
-            } else if (issuer && p.act_mode < 5) {
+            }
+            if (q == 0 && lane < 6 && p.act_mode < 5) {
+              // one lane per output box (c, h, 4 gates): parallel TMA issue
               const int chan = nt * 64 + j0;
-              if (!(p.skip_mask & 1)) tma_store_4d(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff);
-              if (!(p.skip_mask & 2)) tma_store_4d(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff);
-              if (p.gates_boff >= 0 && !(p.skip_mask & 4)) {
-#pragma unroll
-                for (int gt = 0; gt < 4; ++gt)
-                  tma_store_4d(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
+              const int skip = p.skip_mask | p.lsu_mask;
+              if (lane == 0) {
+                if (!(skip & 1)) tma_store_4d(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff);
+              } else if (lane == 1) {
+                if (!(skip & 2)) tma_store_4d(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff);
+              } else if (p.gates_boff >= 0 && !(skip & 4)) {
+                const int gt = lane - 2;
+                tma_store_4d(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
               }
               tma_store_commit();
             }
@@ -577,7 +601,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (acc == 0) acc_phase ^= 1;
         }
       }
-      if (issuer) tma_store_wait_all();  // outstanding bulk stores complete before the CTA retires
+      if (q == 0 && lane < 6) tma_store_wait_all();  // outstanding bulk stores complete before the CTA retires
     } else {
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;

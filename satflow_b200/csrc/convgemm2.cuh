@@ -24,7 +24,7 @@
 
 namespace clstm {
 
-constexpr int kPairMaxAStages = 3;
+constexpr int kPairMaxAStages = 8;
 constexpr int kPairMaxBStages = 8;
 
 // ------------------------------------------------------------------ cluster / cta_group::2 PTX
@@ -100,6 +100,8 @@ struct PairGemmParams {
   int a_slot_bytes;    // max over segments of kh * pitch * 128
   int pitch[2];        // halo row pitch in pixels per segment (multiple of 8)
   int halo_w[2];       // 128 + kw - 1 per segment (TMA box width)
+  int halo;            // 1: halo-stationary A (one load per chunk, taps = shifted descriptors);
+                       // 0: one [128 px x 64 ch] A load per (tap, chunk) like convgemm.cuh
 };
 
 inline size_t pairgemm_smem_bytes(int a_stages, int a_slot_bytes, int b_stages, int n_tile, int n_tiles) {
@@ -186,19 +188,35 @@ pairgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* tmA = (s == 0) ? &tmA0 : &tmA1;
           const ConvSeg sg = p.seg[s];
-          const int row_bytes = pp.halo_w[s] * 128;
-          for (int ch = 0; ch < sg.chunks; ++ch) {
-            mbar_wait(&a_empty[slot], phase ^ 1);
-            uint8_t* dst = smem_a + slot * pp.a_slot_bytes;
-            if (leader) mbar_expect_tx(&a_full[slot], 2 * sg.kh * row_bytes);
-            const uint32_t bar = mapa_u32(smem_u32(&a_full[slot]), 0);
-            for (int r = 0; r < sg.kh; ++r)
-              tma_load_4d_pair(dst + r * pp.pitch[s] * 128, tmA, bar, ch * kBlockK, w0 - sg.kw / 2, h0 + r - sg.kh / 2,
-                               b + sg.b_off);
-            if (++slot == pp.a_stages) {
-              slot = 0;
-              phase ^= 1;
+          if (pp.halo) {
+            const int row_bytes = pp.halo_w[s] * 128;
+            for (int ch = 0; ch < sg.chunks; ++ch) {
+              mbar_wait(&a_empty[slot], phase ^ 1);
+              uint8_t* dst = smem_a + slot * pp.a_slot_bytes;
+              if (leader) mbar_expect_tx(&a_full[slot], 2 * sg.kh * row_bytes);
+              const uint32_t bar = mapa_u32(smem_u32(&a_full[slot]), 0);
+              for (int r = 0; r < sg.kh; ++r)
+                tma_load_4d_pair(dst + r * pp.pitch[s] * 128, tmA, bar, ch * kBlockK, w0 - sg.kw / 2,
+                                 h0 + r - sg.kh / 2, b + sg.b_off);
+              if (++slot == pp.a_stages) {
+                slot = 0;
+                phase ^= 1;
+              }
             }
+          } else {
+            for (int dy = 0; dy < sg.kh; ++dy)
+              for (int dx = 0; dx < sg.kw; ++dx)
+                for (int ch = 0; ch < sg.chunks; ++ch) {
+                  mbar_wait(&a_empty[slot], phase ^ 1);
+                  if (leader) mbar_expect_tx(&a_full[slot], 2 * kABytes);
+                  const uint32_t bar = mapa_u32(smem_u32(&a_full[slot]), 0);
+                  tma_load_4d_pair(smem_a + slot * pp.a_slot_bytes, tmA, bar, ch * kBlockK, w0 + dx - sg.kw / 2,
+                                   h0 + dy - sg.kh / 2, b + sg.b_off);
+                  if (++slot == pp.a_stages) {
+                    slot = 0;
+                    phase ^= 1;
+                  }
+                }
           }
         }
       }
@@ -214,20 +232,21 @@ pairgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSeg sg = p.seg[s];
-          // k-block order inside a segment: chunk-major, then taps (the halo of a chunk serves all its taps)
-          for (int ch = 0; ch < sg.chunks; ++ch)
-            for (int tap = 0; tap < sg.kh * sg.kw; ++tap) {
-              mbar_wait(&b_empty[stage], phase ^ 1);
-              if (leader) mbar_expect_tx(&b_full[stage], 2 * b_stage_bytes);
-              const uint32_t bar = mapa_u32(smem_u32(&b_full[stage]), 0);
-              // packed K order is tap-major: k-block index = seg_base + tap * chunks + ch
-              tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, bar, (kb + tap * sg.chunks + ch) * kBlockK,
-                               nt * p.n_tile + static_cast<int>(rank) * half_rows);
-              if (++stage == pp.b_stages) {
-                stage = 0;
-                phase ^= 1;
-              }
+          // k-block order inside a segment: halo mode = chunk-major then taps (the halo of a chunk serves all
+          // its taps); per-tap mode = the packed order (tap-major).  Packed K index = seg_base + tap*chunks + ch.
+          const int nkb = sg.chunks * sg.kh * sg.kw;
+          for (int i = 0; i < nkb; ++i) {
+            const int kidx = pp.halo ? ((i % (sg.kh * sg.kw)) * sg.chunks + i / (sg.kh * sg.kw)) : i;
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&b_full[stage], 2 * b_stage_bytes);
+            const uint32_t bar = mapa_u32(smem_u32(&b_full[stage]), 0);
+            tma_load_2d_pair(smem_b + stage * b_stage_bytes, &tmB, bar, (kb + kidx) * kBlockK,
+                             nt * p.n_tile + static_cast<int>(rank) * half_rows);
+            if (++stage == pp.b_stages) {
+              stage = 0;
+              phase ^= 1;
             }
+          }
           kb += sg.chunks * sg.kh * sg.kw;
         }
       }
@@ -245,26 +264,29 @@ pairgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         uint32_t first = 1;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSeg sg = p.seg[s];
-          for (int ch = 0; ch < sg.chunks; ++ch) {
+          const int taps = sg.kh * sg.kw;
+          const int items = pp.halo ? sg.chunks : sg.chunks * taps;
+          for (int it = 0; it < items; ++it) {
             mbar_wait(&a_full[slot], a_phase);
             const uint32_t a_base = smem_u32(smem_a + slot * pp.a_slot_bytes);
-            for (int dy = 0; dy < sg.kh; ++dy)
-              for (int dx = 0; dx < sg.kw; ++dx) {
-                mbar_wait(&b_full[stage], b_phase);
-                tcgen05_fence_after();
-                const uint64_t adesc = make_smem_desc_sw128(a_base + (dy * pp.pitch[s] + dx) * 128, 16, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes), 16, 1024);
+            const int ntap = pp.halo ? taps : 1;
+            for (int tp = 0; tp < ntap; ++tp) {
+              const int dy = tp / sg.kw, dx = tp % sg.kw;
+              mbar_wait(&b_full[stage], b_phase);
+              tcgen05_fence_after();
+              const uint64_t adesc = make_smem_desc_sw128(a_base + (dy * pp.pitch[s] + dx) * 128, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * b_stage_bytes), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  umma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                  first = 0;
-                }
-                umma_commit_pair(&b_empty[stage]);
-                if (++stage == pp.b_stages) {
-                  stage = 0;
-                  b_phase ^= 1;
-                }
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                umma_f16_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                first = 0;
               }
+              umma_commit_pair(&b_empty[stage]);
+              if (++stage == pp.b_stages) {
+                stage = 0;
+                b_phase ^= 1;
+              }
+            }
             umma_commit_pair(&a_empty[slot]);
             if (++slot == pp.a_stages) {
               slot = 0;

@@ -43,6 +43,7 @@ struct WgradParams {
   int stages;
   float* partial;  // [splits][n_blocks*128][total_blocks*64] fp32
   int accumulate;  // 0: overwrite, 1: +=
+  int dbg_no_tma;  // experiment: after the first ring fill, reuse shared memory (no TMA) -> pure MMA rate
 };
 
 template <typename E>
@@ -92,7 +93,24 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int my_tiles = (p.num_p_tiles - split + p.splits - 1) / p.splits;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // Lanes 0 .. nblk+1 each own one box of the stage (lane 0/1: the two A boxes, lane 2+j: column block j), so
+    // the boxes of a stage are issued in parallel instead of serially by one thread.
+    if (lane < 2 + nblk) {
+      // per-lane constants of the box this lane loads
+      const CUtensorMap* map = &tmA;
+      int c0 = nb * 128 + lane * 64, dxs = 0, dys = 0, boff = p.a_b_off;
+      if (lane >= 2) {
+        int jj = blk0 + (lane - 2);
+        const int sidx = (jj < p.seg[0].nblk) ? 0 : 1;
+        if (sidx) jj -= p.seg[0].nblk;
+        const WgradSeg sg = p.seg[sidx];
+        const int tap = jj / sg.chunks;
+        map = sidx == 0 ? &tmB0 : &tmB1;
+        c0 = (jj % sg.chunks) * 64;
+        dxs = tap % sg.kw - sg.cx;
+        dys = tap / sg.kw - sg.cy;
+        boff = sg.b_off;
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -103,17 +121,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int w0 = tw * p.BW, h0 = th * p.BH;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* dst = smem + stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
-        tma_load_4d(dst, &tmA, &full_bar[stage], nb * 128, w0, h0, b + p.a_b_off);
-        tma_load_4d(dst + kBoxBytes, &tmA, &full_bar[stage], nb * 128 + 64, w0, h0, b + p.a_b_off);
-        for (int j = 0; j < nblk; ++j) {
-          int jj = blk0 + j;
-          const int sidx = (jj < p.seg[0].nblk) ? 0 : 1;
-          if (sidx) jj -= p.seg[0].nblk;
-          const WgradSeg sg = p.seg[sidx];
-          const int tap = jj / sg.chunks, chunk = jj % sg.chunks;
-          tma_load_4d(dst + (2 + j) * kBoxBytes, sidx == 0 ? &tmB0 : &tmB1, &full_bar[stage], chunk * 64,
-                      w0 + tap % sg.kw - sg.cx, h0 + tap / sg.kw - sg.cy, b + sg.b_off);
+        if (p.dbg_no_tma && it >= p.stages) {
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+        } else {
+          if (lane == 0) mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_4d(dst + lane * kBoxBytes, map, &full_bar[stage], c0, w0 + dxs, h0 + dys, b + boff);
         }
         if (++stage == p.stages) {
           stage = 0;
