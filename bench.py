@@ -231,14 +231,33 @@ def run_ours(args):
     ms_step, launches = timed(lambda: train_step(x_dev, y_dev), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end through the public module API with HOST buffers: pinned H2D of x and target + D2H of the loss
-    def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        td = y_host.to(dev, non_blocking=True)
-        return train_step(xd, td).item()
+    # end to end through the public module API with HOST buffers: every step's x and target are copied from pinned
+    # host memory inside the timed region (double-buffered on a side stream so the copy of step i+1 overlaps
+    # step i, as a DataLoader with pin_memory does) and the loss is read back to the host every step.
+    from satflow_b200.prefetch import DevicePrefetcher
 
-    e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
+    def e2e_run(steps):
+        pf = DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev)
+        out = 0.0
+        for xd, td in pf:
+            loss = train_step(xd, td)
+            pf.done_with_current()
+            out = loss.item()
+        return out
+
+    e2e_run(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    ms_e2e /= args.steps
 
     # inference (BASELINE configs[1]): forward rollout only, same shapes
     extra = {}

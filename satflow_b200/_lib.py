@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclstm.so")
+LIB_PATH = os.environ.get("CLSTM_LIB", os.path.join(_HERE, "libclstm.so"))  # CLSTM_LIB: A/B experiments only
 
 CLSTM_F16 = 0
 CLSTM_BF16 = 1

@@ -20,6 +20,8 @@
 #include "../../include/clstm.h"
 #include "convgemm.cuh"
 #include "convgemm2.cuh"
+#include "convgemm3.cuh"
+#include "dgradT.cuh"
 #include "pointwise.cuh"
 #include "selftest.cuh"
 #include "wgrad.cuh"
@@ -128,20 +130,22 @@ int make_map_act(CUtensorMap* m, int dtype, const void* ptr, int C, int W, int H
 // (c states, dgrad outputs) use 64-byte rows + SWIZZLE_64B, 16-bit tensors (h, gates) 32-byte rows + SWIZZLE_32B,
 // matching the conflict-free staging layout of the convgemm epilogue.  TMA stores clip out-of-bounds pixels.
 int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, int C, int W, int H, long long N,
-                 int boxW, int boxH) {
+                 int boxW, int boxH, int box_c = 16) {
   EncodeTiledFn enc;
   RC_TRY(get_encode(&enc));
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)W * C * elem_bytes,
                            (cuuint64_t)H * W * C * elem_bytes};
-  cuuint32_t box[4] = {16, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
+  const int row_bytes = box_c * elem_bytes;
+  const CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                            : (dtype16 == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                    : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUresult r = enc(m, dt, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(epilogue C=%d W=%d H=%d N=%lld elem %d) -> %d", C, W, H, N,
                 elem_bytes, (int)r);
@@ -154,6 +158,22 @@ inline int weight_boxes(int n_tile) {
   // dgrad 673 -> 890 us); one box issued by its own lane (parallel with the A box) is best.
   const int v = env_int("CLSTM_B_BOXES", 1);
   return (v == 1 || v == 2 || v == 4) && n_tile % (8 * v) == 0 ? v : 1;
+}
+
+// fp32 [N][H][W][C] tensor written in [16 px along W] x 64-channel boxes (256-byte rows, no swizzle): the
+// transposed dgrad's output blocks.
+int make_map_out64(CUtensorMap* m, const void* ptr, int C, int W, int H, long long N) {
+  EncodeTiledFn enc;
+  RC_TRY(get_encode(&enc));
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {64, 16, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(out64 C=%d W=%d H=%d) -> %d", C, W, H, (int)r);
+  return 0;
 }
 
 // Packed weight matrix [rows][K] (K-major); box = 64 k x boxRows rows.
@@ -228,6 +248,7 @@ struct CellState {
   int with_x = 0;
   int n_tile_d = 0;
   int slots_h = 0, slots_c = 0;
+  int h_stride = 1, c_stride = 1;  // slot permutation strides (coprime with the slot counts)
   int wg_total = 0, wg_group = 0, wg_splits = 0;
   bool bwd_started = false;
   // packed parameters
@@ -245,6 +266,9 @@ struct CellState {
   float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
   CUtensorMap m_h128, m_h64, m_hhalo, m_wp, m_wd, m_wp_half, m_wd_half;
+  CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
+  CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
+  CUtensorMap m_c32, m_h32, m_g64;                  // wide-row staged epilogue of the cell kernel
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
@@ -333,15 +357,26 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
                       g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
+  RC_TRY(make_map_epi(&cs.m_c32, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
+                      g.BH, 32));
+  RC_TRY(make_map_epi(&cs.m_h32, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH, 32));
+  if (ctx.training)
+    RC_TRY(make_map_epi(&cs.m_g64, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
+                        g.BW, g.BH, 64));
   if (ctx.training) {
     RC_TRY(make_map_epi(&cs.m_g16, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
                         g.BW, g.BH));
     RC_TRY(make_map_epi(&cs.m_dh16, 4, ctx.dtype, cs.dh_own, ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
+    RC_TRY(make_map_w(&cs.m_wdT, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, 128));
+    RC_TRY(make_map_out64(&cs.m_dhT, cs.dh_own, ctx.HP, g.W, g.H, g.B));
+    if (cs.with_x) RC_TRY(make_map_out64(&cs.m_dxT, cs.dxb, cs.g.CIP, g.W, g.H, g.B));
     if (cs.with_x) RC_TRY(make_map_epi(&cs.m_dx16, 4, ctx.dtype, cs.dxb, cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
   }
   if (ctx.pair_ok) {
     RC_TRY(make_map_act(&cs.m_hhalo, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 128 + cs.g.kw - 1, 1));
     RC_TRY(make_map_w(&cs.m_wp_half, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
+    RC_TRY(make_map_w(&cs.m_wp32, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 32));
+    if (ctx.training) RC_TRY(make_map_w(&cs.m_wd32, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, 32));
     if (ctx.training) RC_TRY(make_map_w(&cs.m_wd_half, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / 2));
   }
   return 0;
@@ -359,6 +394,8 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? (env_int("CLSTM_STAGED", 1) ? 1 : 0) : 0;
   p.b_boxes = weight_boxes(p.n_tile);
   p.prod_serial = env_int("CLSTM_PROD_SERIAL", 0);
+  p.dbg_no_tma = env_int("CLSTM_NOTMA", 0);
+  if (EPI == EPI_STORE) p.skip_mask = env_int("CLSTM_SKIP", 0);
   const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));
@@ -424,6 +461,100 @@ int launch_pairgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   pairgemm_kernel<E, EPI><<<2 * clusters, kGemmThreads, smem, st>>>(a0, a1, b, pp);
   *used = true;
   return after_launch("pairgemm_kernel");
+}
+
+// Two-row halo kernel (convgemm3.cuh).  a0/a1: one-row maps (box 128 + kw - 1 for conv segments, 128 for direct
+// ones); b: 32-row weight boxes; x0..x2: the staged-epilogue maps.
+template <typename E, int EPI>
+int launch_halo2(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                 const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& x2, ConvGemmParams p, const Geo& g,
+                 long long images, cudaStream_t st, bool* used) {
+  *used = false;
+  if (g.BW != 128 || g.BH != 1 || !env_int("CLSTM_HALO2", 1)) return 0;
+  const int n_total = p.n_tiles * p.n_tile;
+  if (EPI == EPI_LSTM && p.n_tile != 256) return 0;
+  if (n_total % 64) return 0;
+  Halo2Params hp;
+  memset(&hp, 0, sizeof(hp));
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  p.staged = 1;
+  hp.n_sub = (EPI == EPI_LSTM) ? 128 : ((n_total % 128 == 0) ? 128 : 64);
+  hp.n_subs = n_total / hp.n_sub;
+  hp.row_pairs = (g.H + 1) / 2;
+  int slot = 0, max_kh = 1;
+  for (int s = 0; s < p.nseg; ++s) {
+    hp.halo_w[s] = 128 + p.seg[s].kw - 1;
+    hp.pitch[s] = round_up(hp.halo_w[s], 8);
+    if (hp.pitch[s] * 128 > slot) slot = hp.pitch[s] * 128;
+    if (p.seg[s].kh > max_kh) max_kh = p.seg[s].kh;
+  }
+  hp.a_row_bytes = slot;
+  const int stg = h2_stg_bytes(EPI);
+  const int bias_floats = p.bias ? n_total : 0;
+  // shared-memory split: at least kh + 3 ring rows and 4 weight stages, then alternate extra stages / rows
+  int rows = max_kh + 3, bst = env_int("CLSTM_H2_BSTAGES", 4);
+  auto fits = [&](int r, int bs) {
+    return halo2_smem_bytes(r, slot, bs, hp.n_sub, stg, bias_floats) <= static_cast<size_t>(dev.smem_optin);
+  };
+  if (!fits(rows, bst)) {
+    rows = max_kh + 2;
+    if (!fits(rows, bst)) return 0;
+  }
+  bool grew = true;
+  while (grew) {
+    grew = false;
+    if (rows < kH2MaxRows && rows < 2 * (max_kh + 1) + 1 && fits(rows + 1, bst)) ++rows, grew = true;
+    if (bst < kH2MaxBStages && fits(rows, bst + 1)) ++bst, grew = true;
+  }
+  hp.a_rows = rows;
+  hp.b_stages = bst;
+  hp.g = p;
+  const size_t smem = halo2_smem_bytes(rows, slot, bst, hp.n_sub, stg, bias_floats);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(halo2_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  const long long units = static_cast<long long>(images) * hp.row_pairs * g.tiles_w * hp.n_subs;
+  const int grid = units < dev.sms ? static_cast<int>(units) : dev.sms;
+  halo2_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0, x1, x2, hp);
+  *used = true;
+  return after_launch("halo2_kernel");
+}
+
+// Transposed dgrad (dgradT.cuh): channels as M, 256 pixels as N.
+template <typename E>
+int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
+                  const CUtensorMap& x1, const ConvSeg& seg, int rows_d, int split_col, const Geo& g, long long images,
+                  cudaStream_t st, bool* used) {
+  *used = false;
+  if (g.BW < 16 || !env_int("CLSTM_DGRADT", 1)) return 0;
+  DgradTParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  p.seg = seg;
+  p.m_tiles = (rows_d + 127) / 128;
+  p.split_col = split_col;
+  p.lbw = 0;
+  while ((1 << p.lbw) < g.BW) ++p.lbw;
+  int stages = (dev.smem_optin - static_cast<int>(dgradT_smem_bytes(0))) / kDtStageBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return 0;
+  p.stages = stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(dgradT_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  const int units = ((p.num_m_tiles + 1) / 2) * p.m_tiles;
+  const int grid = units < dev.sms ? units : dev.sms;
+  dgradT_kernel<E><<<grid, kGemmThreads, dgradT_smem_bytes(stages), st>>>(dz128, wT, x0, x1, p);
+  *used = true;
+  return after_launch("dgradT_kernel");
 }
 
 template <typename E>
@@ -518,6 +649,12 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
     p.cnext_boff = cnext_slot * ctx.geo.B;
     p.hnext_boff = sn * ctx.geo.B;
     p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
+    if (ctx.pair_ok && env_int("CLSTM_HALO2_FWD", 0)) {
+      bool used = false;
+      RC_TRY((launch_halo2<E, EPI_LSTM>(ctx.dev, *in.maphalo, cs.m_hhalo, cs.m_wp32, cs.m_c16, cs.m_h16,
+                                        ctx.training ? cs.m_g16 : cs.m_h16, p, ctx.geo, ctx.geo.B, st, &used)));
+      if (used) return 0;
+    }
     return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
                                         &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16);
   }
@@ -552,6 +689,18 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
   p.ld0 = g.CIP;
   p.ld1 = ctx.HP;
   p.out_scale = 1.f;
+  {
+    bool used = false;
+    RC_TRY((launch_dgradT<E>(ctx.dev, ctx.m_dz128, cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
+                             cs.rows_d, p.split_col, ctx.geo, ctx.geo.B, st, &used)));
+    if (used) return 0;
+  }
+  if (ctx.pair_ok && env_int("CLSTM_HALO2_DGRAD", 0)) {
+    bool used = false;
+    RC_TRY((launch_halo2<E, EPI_STORE>(ctx.dev, ctx.m_dzhalo, ctx.m_dzhalo, cs.m_wd32, cs.with_x ? cs.m_dx16 : cs.m_dh16,
+                                       cs.m_dh16, cs.m_dh16, p, ctx.geo, ctx.geo.B, st, &used)));
+    if (used) return 0;
+  }
   if (ctx.pair_ok) {
     bool used = false;
     const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
@@ -680,8 +829,25 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
 }
 
 // slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
-inline int hslot(const CellState& cs, int s) { return s % cs.slots_h; }
-inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
+// Memory slot of a state after `s` steps.  Full stacks are PERMUTED: consecutive time steps live
+// slot_stride slots apart (mod the slot count).  Measured on B200 (DESIGN.md §4 "slot placement"): a cell step
+// that reads h slot m while writing h slot m +- 1 (128 MB away) loses ~100 us to the write stream; 3 slots
+// apart costs ~15 us.
+inline int hslot(const CellState& cs, int s) { return (s % cs.slots_h) * cs.h_stride % cs.slots_h; }
+inline int cslot(const CellState& cs, int s) { return (s % cs.slots_c) * cs.c_stride % cs.slots_c; }
+inline int pick_stride(int slots, int want) {
+  if (slots <= 3 || want <= 1) return 1;
+  auto gcd = [](int a, int b) {
+    while (b) {
+      const int t = a % b;
+      a = b, b = t;
+    }
+    return a;
+  };
+  for (int k = want; k < slots; ++k)
+    if (gcd(k, slots) == 1) return k;
+  return 1;
+}
 
 // Input of cell k at its step t (conv_lstm.py:176-196).
 InputRef plan_input(clstm_plan* p, int k, int t) {
@@ -753,22 +919,26 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
     for (int l = 0; l < L; ++l) RC_TRY(step(l, t));
   for (int t = 0; t < c.t_out; ++t)  // conv_lstm.py:188-196
     for (int l = 0; l < L; ++l) RC_TRY(step(L + l, t));
-  // head: Conv3d(1,3,3) + Sigmoid over the stacked last-decoder h (conv_lstm.py:198-201)
+  // head: Conv3d(1,3,3) + Sigmoid over the last-decoder h of every output step (conv_lstm.py:198-201).  The
+  // h slots are permuted in memory, so the head runs once per output frame (B images each) and writes frame t
+  // of y directly — the reference's stack / permute copies (:198-199) never exist.
   {
-    ConvGemmParams hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.n_tile = p->NT;
-    hp.n_tiles = 1;
-    hp.nseg = 1;
-    hp.seg[0] = ConvSeg{HP / 64, 3, 3, 1 * c.batch};  // slots 1..T_out
-    hp.bias = p->bias_h;
-    hp.y = y;
-    hp.c_out = c.out_channels;
-    hp.t_out = c.t_out;
-    hp.b_img = c.batch;
     const CellState& last = p->cells[p->ncell - 1];
-    RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo,
-                                         static_cast<long long>(c.t_out) * c.batch, st)));
+    for (int t = 0; t < c.t_out; ++t) {
+      ConvGemmParams hp;
+      memset(&hp, 0, sizeof(hp));
+      hp.n_tile = p->NT;
+      hp.n_tiles = 1;
+      hp.nseg = 1;
+      hp.seg[0] = ConvSeg{HP / 64, 3, 3, hslot(last, t + 1) * c.batch};
+      hp.bias = p->bias_h;
+      hp.y = y;
+      hp.c_out = c.out_channels;
+      hp.t_out = c.t_out;
+      hp.b_img = c.batch;
+      hp.t0 = t;
+      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo, c.batch, st)));
+    }
   }
   p->forward_done = true;
   return 0;
@@ -1086,6 +1256,8 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
     const bool full = cfg->training || k == p->ncell - 1;  // the head reads every last-decoder h
     cs.slots_h = full ? T + 1 : 2;
     cs.slots_c = cfg->training ? T + 1 : 2;
+    cs.h_stride = pick_stride(cs.slots_h, env_int("CLSTM_SLOT_STRIDE", 1));
+    cs.c_stride = pick_stride(cs.slots_c, env_int("CLSTM_CSLOT_STRIDE", 1));
   }
   int nt = 256;
   while (ctx.HP % nt) nt -= 64;

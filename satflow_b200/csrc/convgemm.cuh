@@ -59,6 +59,7 @@ struct ConvGemmParams {
   int nseg;
   ConvSeg seg[2];
   int stages;
+  int dbg_no_tma;   // experiment: after the first ring fill reuse shared memory (no TMA loads) -> pure MMA rate
   int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
   int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
   // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
@@ -83,7 +84,7 @@ struct ConvGemmParams {
   float out_scale;
   // ---- EPI_HEAD (n_tile == C_out rounded up to 16)
   float* y;  // (Bimg, C_out, T, H, W); the maps' batch index is t * Bimg + b
-  int c_out, t_out, b_img;
+  int c_out, t_out, b_img, t0;  // output frame of image b is t0 + b / b_img
 };
 
 // Epilogue of one 128-pixel x n_tile accumulator tile for the calling warp: TMEM -> registers -> fused
@@ -217,7 +218,7 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
     }
   } else {  // EPI_HEAD
     const int groups = p.n_tile / 16;
-    const int t = b / p.b_img, bi = b % p.b_img;
+    const int t = p.t0 + b / p.b_img, bi = b % p.b_img;
     const size_t plane = static_cast<size_t>(p.H) * p.W;
 #pragma unroll 1
     for (int g = half; g < groups; g += 2) {
@@ -312,7 +313,9 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int ch = 0; ch < sg.chunks; ++ch, ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* a_dst = smem + stage * stage_bytes;
-                if (lane == 0) {
+                if (p.dbg_no_tma && (tile != static_cast<int>(blockIdx.x) || kb >= p.stages)) {
+                  if (lane == 0) mbar_arrive(&full_bar[stage]);
+                } else if (lane == 0) {
                   mbar_expect_tx(&full_bar[stage], stage_bytes);
                   tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
                               h0 + dy - sg.kh / 2, b + sg.b_off);
@@ -588,7 +591,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                               __uint_as_float(v[4 * j + 2]) * p.out_scale, __uint_as_float(v[4 * j + 3]) * p.out_scale);
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
-            if (issuer) {
+            if (issuer && !(p.skip_mask & 1)) {
               const int col = nt * p.n_tile + g * 16;
               if (col < p.split_col)
                 tma_store_4d(&tmX0, stg, col, w0, h0, b);
