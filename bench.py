@@ -271,29 +271,46 @@ def run_ours(args):
         extra["inference"] = {"frames_per_s": world * B * (t_in + t_out) / ms_inf * 1e3, "ms_per_step": ms_inf,
                               "tflops": algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW) / ms_inf / 1e9}
 
-    # roofline of the dominant kernel: the fused cell step (implicit-GEMM conv + LSTM epilogue), timed alone
+    # roofline of the dominant kernel: the fused cell step (implicit-GEMM conv + LSTM epilogue), timed alone with CUDA
+    # events on the launching stream through the C-ABI measurement hook; the other kernels of the step alongside.
     peaks = measured_peaks()
     roof = None
     cpu = None
     if rank == 0:
         plan = [p for p in model.model._plans.values() if p.training][0]
-        reps = 20
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3):
-            plan.profile_cell_step(3, 5)
-        e0.record()
-        for _ in range(reps):
-            plan.profile_cell_step(3, 5)  # decoder_2 step 5: K = (64 + 64) * 9
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        fl = cell_step_flops(B, hid, hid, HW, HW)
+
+        def time_kernel(kind, cell, step, reps=20):
+            for _ in range(3):
+                plan.profile_kernel(kind, cell, step)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                plan.profile_kernel(kind, cell, step)
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / reps
+
+        fl = cell_step_flops(B, hid, hid, HW, HW)  # decoder_2: K = (64 + 64) * 9
+        k_ms = time_kernel("cell_fwd", 3, 5)
         ach = fl / k_ms / 1e9
         roof = {"kernel": "convgemm_kernel<EPI_LSTM> (fused cell step, training variant: also writes gates)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_burst"], "traffic": None, "launch_ms": k_ms,
-                "flops_per_launch": fl, "peak_source": peaks["source"] + " burst, kernel timed alone"}
+                "frac": ach / peaks["bf16_burst"], "traffic": 1.43e9, "launch_ms": k_ms,
+                "flops_per_launch": fl, "peak_source": peaks["source"] + " burst, kernel timed alone",
+                "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r1_ncu_full_summary.csv)"}
+        others = []
+        for kind, name in (("dgrad", "dgradT_kernel (data gradient)"), ("wgrad", "wgrad_kernel (weight gradient)")):
+            ms = time_kernel(kind, 3, 5)
+            others.append({"kernel": name, "bound": "tensor", "achieved": fl / ms / 1e9, "peak": peaks["bf16_burst"],
+                           "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peaks["bf16_burst"], "launch_ms": ms})
+        npix = B * HW * HW
+        gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
+        ms = time_kernel("gate_grad", 3, 5)
+        others.append({"kernel": "gate_grad_kernel (pointwise gate gradient)", "bound": "hbm",
+                       "achieved": gg_bytes / ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                       "frac": gg_bytes / ms / 1e6 / peaks["hbm"], "launch_ms": ms})
+        extra["kernels"] = others
         flops_step = 3 * algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW)
         extra["step_tflops"] = flops_step * world / ms_step / 1e9
         extra["step_frac_of_sustained_peak"] = flops_step / ms_step / 1e9 / peaks["bf16_sustained"]

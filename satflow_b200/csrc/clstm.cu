@@ -395,6 +395,9 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.b_boxes = weight_boxes(p.n_tile);
   p.prod_serial = env_int("CLSTM_PROD_SERIAL", 0);
   p.dbg_no_tma = env_int("CLSTM_NOTMA", 0);
+  p.hint_store = env_int("CLSTM_HINT_STORE", 0);
+  p.hint_w = env_int("CLSTM_HINT_W", 0);
+  p.hint_a = env_int("CLSTM_HINT_A", 0);
   if (EPI == EPI_STORE) p.skip_mask = env_int("CLSTM_SKIP", 0);
   const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;

@@ -59,6 +59,7 @@ struct ConvGemmParams {
   int nseg;
   ConvSeg seg[2];
   int stages;
+  int hint_store, hint_w, hint_a;  // L2 cache hints: 0 none, 1 evict_first, 2 evict_last (stores / weights / A tiles)
   int dbg_no_tma;   // experiment: after the first ring fill reuse shared memory (no TMA loads) -> pure MMA rate
   int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
   int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
@@ -317,16 +318,24 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   if (lane == 0) mbar_arrive(&full_bar[stage]);
                 } else if (lane == 0) {
                   mbar_expect_tx(&full_bar[stage], stage_bytes);
-                  tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
-                              h0 + dy - sg.kh / 2, b + sg.b_off);
+                  if (p.hint_a)
+                    tma_load_4d_hint(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
+                                     h0 + dy - sg.kh / 2, b + sg.b_off, p.hint_a == 1 ? kEvictFirst : kEvictLast);
+                  else
+                    tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
+                                h0 + dy - sg.kh / 2, b + sg.b_off);
                   if (p.prod_serial)
                     for (int part = 0; part < p.b_boxes; ++part)
                       tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
                                   nt * p.n_tile + part * b_rows);
                 } else {
                   const int part = lane - 1;
-                  tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
-                              nt * p.n_tile + part * b_rows);
+                  if (p.hint_w)
+                    tma_load_2d_hint(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
+                                     nt * p.n_tile + part * b_rows, p.hint_w == 1 ? kEvictFirst : kEvictLast);
+                  else
+                    tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
+                                nt * p.n_tile + part * b_rows);
                 }
                 if (++stage == p.stages) {
                   stage = 0;
@@ -550,13 +559,14 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               // one lane per output box (c, h, 4 gates): parallel TMA issue
               const int chan = nt * 64 + j0;
               const int skip = p.skip_mask | p.lsu_mask;
+              const uint64_t pol = p.hint_store == 1 ? kEvictFirst : (p.hint_store == 2 ? kEvictLast : kEvictNormal);
               if (lane == 0) {
-                if (!(skip & 1)) tma_store_4d(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff);
+                if (!(skip & 1)) tma_store_4d_hint(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff, pol);
               } else if (lane == 1) {
-                if (!(skip & 2)) tma_store_4d(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff);
+                if (!(skip & 2)) tma_store_4d_hint(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff, pol);
               } else if (p.gates_boff >= 0 && !(skip & 4)) {
                 const int gt = lane - 2;
-                tma_store_4d(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
+                tma_store_4d_hint(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff, pol);
               }
               tma_store_commit();
             }
