@@ -268,7 +268,6 @@ struct CellState {
   CUtensorMap m_h128, m_h64, m_hhalo, m_wp, m_wd, m_wp_half, m_wd_half;
   CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
-  CUtensorMap m_c32, m_h32, m_g64;                  // wide-row staged epilogue of the cell kernel
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
@@ -357,12 +356,6 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
                       g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
-  RC_TRY(make_map_epi(&cs.m_c32, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
-                      g.BH, 32));
-  RC_TRY(make_map_epi(&cs.m_h32, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH, 32));
-  if (ctx.training)
-    RC_TRY(make_map_epi(&cs.m_g64, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
-                        g.BW, g.BH, 64));
   if (ctx.training) {
     RC_TRY(make_map_epi(&cs.m_g16, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
                         g.BW, g.BH));
