@@ -249,6 +249,7 @@ struct CellState {
   int n_tile_d = 0;
   int slots_h = 0, slots_c = 0;
   int h_stride = 1, c_stride = 1;  // slot permutation strides (coprime with the slot counts)
+  int h_rot = 0;                   // per-cell rotation of the h slots (full stacks only)
   int wg_total = 0, wg_group = 0, wg_splits = 0;
   bool bwd_started = false;
   // packed parameters
@@ -268,7 +269,8 @@ struct CellState {
   CUtensorMap m_h128, m_h64, m_hhalo, m_wp, m_wd, m_wp_half, m_wd_half;
   CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
-  CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
+  CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue
+  std::vector<CUtensorMap> m_c16s, m_h16s, m_g16s;   // the same, one map per slot / step (N = B images, offset 0) (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
 };
@@ -365,6 +367,26 @@ int map_cell(CellState& cs, const Ctx& ctx) {
     if (cs.with_x) RC_TRY(make_map_out64(&cs.m_dxT, cs.dxb, cs.g.CIP, g.W, g.H, g.B));
     if (cs.with_x) RC_TRY(make_map_epi(&cs.m_dx16, 4, ctx.dtype, cs.dxb, cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
   }
+  if (env_int("CLSTM_SLOT_MAPS", 0)) {
+    // One store map per slot: measured 35 us faster per cell step than one map over the whole stack with an image
+    // offset (finding 2).
+    const size_t npix = g.npix();
+    cs.m_h16s.resize(cs.slots_h);
+    for (int sl = 0; sl < cs.slots_h; ++sl)
+      RC_TRY(make_map_epi(&cs.m_h16s[sl], 2, ctx.dtype, static_cast<uint8_t*>(cs.h) + static_cast<size_t>(sl) * npix * ctx.HP * 2,
+                          ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
+    cs.m_c16s.resize(cs.slots_c);
+    for (int sl = 0; sl < cs.slots_c; ++sl)
+      RC_TRY(make_map_epi(&cs.m_c16s[sl], 4, ctx.dtype, cs.c + static_cast<size_t>(sl) * npix * ctx.HP, ctx.HP, g.W, g.H,
+                          g.B, g.BW, g.BH));
+    if (ctx.training) {
+      cs.m_g16s.resize(cs.T);
+      for (int t = 0; t < cs.T; ++t)
+        RC_TRY(make_map_epi(&cs.m_g16s[t], 2, ctx.dtype,
+                            static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * ctx.HP * 2, 4 * ctx.HP,
+                            g.W, g.H, g.B, g.BW, g.BH));
+    }
+  }
   if (ctx.pair_ok) {
     RC_TRY(make_map_act(&cs.m_hhalo, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 128 + cs.g.kw - 1, 1));
     RC_TRY(make_map_w(&cs.m_wp_half, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
@@ -379,7 +401,8 @@ int map_cell(CellState& cs, const Ctx& ctx) {
 template <typename E, int EPI>
 int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                     ConvGemmParams p, const Geo& g, long long images, cudaStream_t st,
-                    const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr) {
+                    const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr,
+                    const CUtensorMap* x3 = nullptr) {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
@@ -410,7 +433,8 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   }
   const int total = p.num_m_tiles * p.n_tiles;
   const int grid = total < dev.sms ? total : dev.sms;
-  convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0 ? *x0 : b, x1 ? *x1 : b, x2 ? *x2 : b, p);
+  convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0 ? *x0 : b, x1 ? *x1 : b, x2 ? *x2 : b,
+                                                            x3 ? *x3 : (x0 ? *x0 : b), p);
   return after_launch("convgemm_kernel");
 }
 
@@ -651,6 +675,24 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
                                         ctx.training ? cs.m_g16 : cs.m_h16, p, ctx.geo, ctx.geo.B, st, &used)));
       if (used) return 0;
     }
+    if (!cs.m_h16s.empty()) {  // per-slot epilogue maps: every image offset becomes 0
+      const CUtensorMap* mcp = &cs.m_c16s[cnext_slot];
+      if (p.cprev_boff >= 0) {
+        mcp = &cs.m_c16s[cprev_slot];
+        p.cprev_boff = 0;
+      }
+      const CUtensorMap* mc = &cs.m_c16s[cnext_slot];
+      p.cnext_boff = 0;
+      const CUtensorMap* mh = &cs.m_h16s[sn];
+      p.hnext_boff = 0;
+      const CUtensorMap* mg = mh;
+      if (p.gates_boff >= 0) {
+        mg = &cs.m_g16s[gates_step];
+        p.gates_boff = 0;
+      }
+      return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, mc, mh, mg,
+                                          mcp);
+    }
     return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
                                         &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16);
   }
@@ -829,7 +871,7 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
 // slot_stride slots apart (mod the slot count).  Measured on B200 (DESIGN.md §4 "slot placement"): a cell step
 // that reads h slot m while writing h slot m +- 1 (128 MB away) loses ~100 us to the write stream; 3 slots
 // apart costs ~15 us.
-inline int hslot(const CellState& cs, int s) { return (s % cs.slots_h) * cs.h_stride % cs.slots_h; }
+inline int hslot(const CellState& cs, int s) { return ((s % cs.slots_h) * cs.h_stride + cs.h_rot) % cs.slots_h; }
 inline int cslot(const CellState& cs, int s) { return (s % cs.slots_c) * cs.c_stride % cs.slots_c; }
 inline int pick_stride(int slots, int want) {
   if (slots <= 3 || want <= 1) return 1;
@@ -899,7 +941,11 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
   }
   if (!c.training) {
     // ring-buffered states: slot 0 must read as the zero initial state (layers/ConvLSTM.py:59-64)
-    for (int k = 0; k < p->ncell; ++k) CU_TRY(cudaMemsetAsync(p->cells[k].h, 0, npix * HP * 2, st));
+    for (int k = 0; k < p->ncell; ++k) {
+      CellState& cs = p->cells[k];
+      CU_TRY(cudaMemsetAsync(static_cast<uint8_t*>(cs.h) + static_cast<size_t>(hslot(cs, 0)) * npix * HP * 2, 0,
+                             npix * HP * 2, st));
+    }
   }
   auto step = [&](int k, int t) -> int {
     CellState& cs = p->cells[k];
@@ -1253,6 +1299,7 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
     cs.slots_h = full ? T + 1 : 2;
     cs.slots_c = cfg->training ? T + 1 : 2;
     cs.h_stride = pick_stride(cs.slots_h, env_int("CLSTM_SLOT_STRIDE", 1));
+    cs.h_rot = cs.slots_h > 3 ? (env_int("CLSTM_SLOT_ROT", 0) * k) % cs.slots_h : 0;
     cs.c_stride = pick_stride(cs.slots_c, env_int("CLSTM_CSLOT_STRIDE", 1));
   }
   int nt = 256;
@@ -1293,7 +1340,8 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   // tensor map may read before it is written
   for (int k = 0; k < p->ncell; ++k) {
     CellState& cs = p->cells[k];
-    CU_TRY(cudaMemsetAsync(cs.h, 0, npix * ctx.HP * 2, st));
+    CU_TRY(cudaMemsetAsync(static_cast<uint8_t*>(cs.h) + static_cast<size_t>(hslot(cs, 0)) * npix * ctx.HP * 2, 0,
+                           npix * ctx.HP * 2, st));
     CU_TRY(cudaMemsetAsync(cs.c, 0, npix * ctx.HP * 4, st));
     RC_TRY(map_cell(cs, ctx));
   }

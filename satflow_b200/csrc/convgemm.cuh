@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX0,
                 const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
-                const ConvGemmParams p) {
+                const __grid_constant__ CUtensorMap tmX3, const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kABytes + p.n_tile * 128;
@@ -411,7 +411,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           int nt, w0, h0, b;
           coords(blockIdx.x, nt, w0, h0, b);
           mbar_expect_tx(&cprev_full[half], 8192);
-          tma_load_4d(stg + kStgCprev, &tmX0, &cprev_full[half], nt * 64 + half * 32, w0, h0, b + p.cprev_boff);
+          tma_load_4d(stg + kStgCprev, &tmX3, &cprev_full[half], nt * 64 + half * 32, w0, h0, b + p.cprev_boff);
         }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           int nt, w0, h0, b;
@@ -452,7 +452,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
               if (tn < total_tiles) {
                 mbar_expect_tx(&cprev_full[half], 8192);
-                tma_load_4d(stg + kStgCprev, &tmX0, &cprev_full[half], ntn * 64 + j0n, w0n, h0n, bn + p.cprev_boff);
+                tma_load_4d(stg + kStgCprev, &tmX3, &cprev_full[half], ntn * 64 + j0n, w0n, h0n, bn + p.cprev_boff);
               }
             }
             tmem_ld_wait();

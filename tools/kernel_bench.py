@@ -22,13 +22,13 @@ def main():
     for kind in kinds:
         for cell in ((0, 3) if kind in ("cell_fwd", "wgrad") else (3,)):
             for _ in range(3):
-                plan.profile_kernel(kind, cell, 2)
+                plan.profile_kernel(kind, cell, int(os.environ.get("KB_STEP", "2")) if cell == 3 else 2)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 20
             e0.record()
             for _ in range(reps):
-                plan.profile_kernel(kind, cell, 2)
+                plan.profile_kernel(kind, cell, int(os.environ.get("KB_STEP", "2")) if cell == 3 else 2)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
