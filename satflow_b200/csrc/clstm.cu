@@ -270,7 +270,8 @@ struct CellState {
   CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue
-  std::vector<CUtensorMap> m_c16s, m_h16s, m_g16s;   // the same, one map per slot / step (N = B images, offset 0) (staged store / c_prev load) maps
+  std::vector<CUtensorMap> m_c16s, m_h16s, m_g16s;   // the same, one map per slot / step (N = B images, offset 0)
+  std::vector<CUtensorMap> m_h128s;                  // per-slot A-operand load maps (experiment) (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
 };
@@ -374,6 +375,10 @@ int map_cell(CellState& cs, const Ctx& ctx) {
     cs.m_h16s.resize(cs.slots_h);
     for (int sl = 0; sl < cs.slots_h; ++sl)
       RC_TRY(make_map_epi(&cs.m_h16s[sl], 2, ctx.dtype, static_cast<uint8_t*>(cs.h) + static_cast<size_t>(sl) * npix * ctx.HP * 2,
+                          ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
+    cs.m_h128s.resize(cs.slots_h);
+    for (int sl = 0; sl < cs.slots_h; ++sl)
+      RC_TRY(make_map_act(&cs.m_h128s[sl], ctx.dtype, static_cast<uint8_t*>(cs.h) + static_cast<size_t>(sl) * npix * ctx.HP * 2,
                           ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
     cs.m_c16s.resize(cs.slots_c);
     for (int sl = 0; sl < cs.slots_c; ++sl)
@@ -689,6 +694,11 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
       if (p.gates_boff >= 0) {
         mg = &cs.m_g16s[gates_step];
         p.gates_boff = 0;
+      }
+      if (env_int("CLSTM_SLOT_MAPS", 0) >= 2) {  // also read own h_prev through a per-slot map
+        p.seg[1].b_off = 0;
+        return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128s[sp], cs.m_wp, p, ctx.geo, ctx.geo.B, st, mc, mh,
+                                            mg, mcp);
       }
       return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, mc, mh, mg,
                                           mcp);

@@ -80,37 +80,64 @@ row_im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1
     }
     lut[k] = off;
   }
-  const int total = kh * C * WP;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int wcol = i % WP;
-    const int c = (i / WP) % C;
-    const int r = i / (WP * C);
-    const int hy = h + r - kh / 2, wx = wcol - kw / 2;
-    float val = 0.f;
-    if (hy >= 0 && hy < H && wx >= 0 && wx < W) {
-      if (MODE == 0) {
-        val = __ldg(src0 + (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W + wx);
-      } else {
-        const size_t g = (((static_cast<size_t>(b) * C + c) * T + t) * H + hy) * W + wx;
-        const float yy = __ldg(src1 + g);
-        val = __ldg(src0 + g) * yy * (1.f - yy) * scale;
-      }
+  // Stage the source rows: one warp per (row, channel) line, lanes along W -> no per-element divisions and
+  // up to WP/32 independent, fully coalesced loads in flight per lane.
+  const int lines = kh * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int ln = warp; ln < lines; ln += nwarps) {
+    const int c = ln % C, r = ln / C;
+    const int hy = h + r - kh / 2;
+    E* dst = sm + static_cast<size_t>(ln) * WP;
+    if (hy < 0 || hy >= H) {
+      for (int wcol = lane; wcol < WP; wcol += 32) dst[wcol] = Elem<E>::from_float(0.f);
+      continue;
     }
-    sm[i] = Elem<E>::from_float(val);
+    const size_t base = (MODE == 0) ? (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W
+                                    : (((static_cast<size_t>(b) * C + c) * T + t) * H + hy) * W;
+#pragma unroll 4
+    for (int wcol = lane; wcol < WP; wcol += 32) {
+      const int wx = wcol - kw / 2;
+      float val = 0.f;
+      if (wx >= 0 && wx < W) {
+        if (MODE == 0) {
+          val = __ldg(src0 + base + wx);
+        } else {
+          const float yy = __ldg(src1 + base + wx);
+          val = __ldg(src0 + base + wx) * yy * (1.f - yy) * scale;
+        }
+      }
+      dst[wcol] = Elem<E>::from_float(val);
+    }
   }
   __syncthreads();
   const int chunks = KP / 8;
   uint4* orow = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(tt) * B + b) * H + h) * static_cast<size_t>(W) * KP);
   const E zero = Elem<E>::from_float(0.f);
-  for (int i = threadIdx.x; i < W * chunks; i += blockDim.x) {
-    const int ck = i % chunks, w = i / chunks;
-    alignas(16) E v[8];
+  if (blockDim.x % chunks == 0) {
+    // fast path: a thread owns one 8-element chunk index for every pixel it visits -> its 8 tap offsets live in
+    // registers and the inner loop is 8 shared-memory reads + one 16-byte store
+    const int ck = threadIdx.x % chunks;
+    int off[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int off = lut[ck * 8 + e];
-      v[e] = off >= 0 ? sm[off + w] : zero;
+    for (int e = 0; e < 8; ++e) off[e] = lut[ck * 8 + e];
+    const int wstep = blockDim.x / chunks;
+    for (int w = threadIdx.x / chunks; w < W; w += wstep) {
+      alignas(16) E v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? sm[off[e] + w] : zero;
+      orow[w * chunks + ck] = *reinterpret_cast<const uint4*>(v);
     }
-    orow[i] = *reinterpret_cast<const uint4*>(v);
+  } else {
+    for (int i = threadIdx.x; i < W * chunks; i += blockDim.x) {
+      const int ck = i % chunks, w = i / chunks;
+      alignas(16) E v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int o = lut[ck * 8 + e];
+        v[e] = o >= 0 ? sm[o + w] : zero;
+      }
+      orow[i] = *reinterpret_cast<const uint4*>(v);
+    }
   }
 }
 
