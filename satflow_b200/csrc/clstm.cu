@@ -266,7 +266,7 @@ struct CellState {
   float* dc = nullptr;      // fp32 [npix][HP]
   float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
-  CUtensorMap m_h128, m_h64, m_hhalo, m_wp, m_wd, m_wp_half, m_wd_half;
+  CUtensorMap m_h128, m_h64, m_hhalo, m_hhalo3, m_wp, m_wd, m_wp_half, m_wd_half;
   CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue
@@ -394,6 +394,7 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   }
   if (ctx.pair_ok) {
     RC_TRY(make_map_act(&cs.m_hhalo, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 128 + cs.g.kw - 1, 1));
+    RC_TRY(make_map_act(&cs.m_hhalo3, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 130, 1));  // the head's 3x3 conv
     RC_TRY(make_map_w(&cs.m_wp_half, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
     RC_TRY(make_map_w(&cs.m_wp32, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 32));
     if (ctx.training) RC_TRY(make_map_w(&cs.m_wd32, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, 32));
@@ -498,14 +499,18 @@ int launch_halo2(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap
   if (g.BW != 128 || g.BH != 1 || !env_int("CLSTM_HALO2", 1)) return 0;
   const int n_total = p.n_tiles * p.n_tile;
   if (EPI == EPI_LSTM && p.n_tile != 256) return 0;
-  if (n_total % 64) return 0;
+  if (EPI == EPI_HEAD) {
+    if (n_total > 32) return 0;  // one weight box of <= 32 rows
+  } else if (n_total % 64) {
+    return 0;
+  }
   Halo2Params hp;
   memset(&hp, 0, sizeof(hp));
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
-  p.staged = 1;
-  hp.n_sub = (EPI == EPI_LSTM) ? 128 : ((n_total % 128 == 0) ? 128 : 64);
+  p.staged = (EPI == EPI_HEAD) ? 0 : 1;
+  hp.n_sub = (EPI == EPI_LSTM) ? 128 : (EPI == EPI_HEAD ? n_total : ((n_total % 128 == 0) ? 128 : 64));
   hp.n_subs = n_total / hp.n_sub;
   hp.row_pairs = (g.H + 1) / 2;
   int slot = 0, max_kh = 1;
@@ -976,7 +981,9 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
   // of y directly — the reference's stack / permute copies (:198-199) never exist.
   {
     const CellState& last = p->cells[p->ncell - 1];
-    for (int t = 0; t < c.t_out; ++t) {
+    const bool contiguous = (last.h_stride == 1 && last.h_rot == 0);  // slots 1..T_out adjacent in memory
+    const int launches = contiguous ? 1 : c.t_out;
+    for (int t = 0; t < launches; ++t) {
       ConvGemmParams hp;
       memset(&hp, 0, sizeof(hp));
       hp.n_tile = p->NT;
@@ -989,7 +996,14 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
       hp.t_out = c.t_out;
       hp.b_img = c.batch;
       hp.t0 = t;
-      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo, c.batch, st)));
+      const long long images = contiguous ? static_cast<long long>(c.t_out) * c.batch : c.batch;
+      if (ctx.pair_ok && env_int("CLSTM_HALO2_HEAD", 0)) {
+        bool used = false;
+        RC_TRY((launch_halo2<E, EPI_HEAD>(ctx.dev, last.m_hhalo3, last.m_hhalo3, p->m_wh, p->m_wh, p->m_wh, p->m_wh, hp, geo,
+                                          images, st, &used)));
+        if (used) continue;
+      }
+      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo, images, st)));
     }
   }
   p->forward_done = true;

@@ -132,7 +132,8 @@ halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     }
   } else if (warp == 3) {
     // ===================== weight producer: n_sub / 32 boxes of 32 rows per stage, one lane each =============
-    const int boxes = hp.n_sub / 32;
+    const int box_rows = hp.n_sub < 32 ? hp.n_sub : 32;
+    const int boxes = hp.n_sub / box_rows;
     if (lane < boxes) {
       uint32_t idx = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -142,7 +143,7 @@ halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         if constexpr (EPI == EPI_LSTM)
           row = (ns >> 1) * 256 + lane * 64 + (ns & 1) * 32;  // gate `lane`, 32-channel half of the 64-channel block
         else
-          row = ns * hp.n_sub + lane * 32;
+          row = ns * hp.n_sub + lane * box_rows;
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSeg sg = p.seg[s];
@@ -153,7 +154,7 @@ halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
               mbar_wait(&b_empty[stage], phase ^ 1);
               if (lane == 0) mbar_expect_tx(&b_full[stage], b_stage_bytes);
               // packed K order is tap-major inside a segment: k-block = seg base + tap * chunks + ch
-              tma_load_2d(smem_b + stage * b_stage_bytes + lane * 32 * 128, &tmB, &b_full[stage],
+              tma_load_2d(smem_b + stage * b_stage_bytes + lane * box_rows * 128, &tmB, &b_full[stage],
                           (kb + tap * sg.chunks + ch) * kBlockK, row);
             }
           kb += sg.chunks * taps;
@@ -311,6 +312,32 @@ halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
               tma_store_4d(&tmX2, stg + kH2G + gt * 4096, gt * p.ldc + chan, w0, hy, b + p.gates_boff);
             }
             tma_store_commit();
+          }
+        }
+      } else if constexpr (EPI == EPI_HEAD) {
+        // bias + sigmoid, written straight into y (B, C_out, T, H, W): 32 consecutive pixels per warp and channel
+        const int groups = hp.n_sub / 16;
+        const int t = p.t0 + b / p.b_img, bi = b % p.b_img;
+        const size_t plane = static_cast<size_t>(p.H) * p.W;
+#pragma unroll 1
+        for (int g = 0; g < groups; ++g) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 16, v);
+          tmem_ld_wait();
+          if (g == groups - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (valid) {
+            float* ybase = p.y + ((static_cast<size_t>(bi) * p.c_out) * p.t_out + t) * plane +
+                           static_cast<size_t>(hy) * p.W + wx;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int co = ns * hp.n_sub + g * 16 + e;
+              if (co < p.c_out)
+                ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(__uint_as_float(v[e]) + bias_s[co]);
+            }
           }
         }
       } else {  // EPI_STORE
