@@ -232,10 +232,16 @@ struct Ctx {
   int HP = 0;
   int training = 0;
   float grad_scale = 0.f;
-  void* dz = nullptr;      // E [npix][4HP]
+  void* dz = nullptr;      // E [npix][4HP]  (buffer 0; == dzb[0])
+  void* dzb[2] = {nullptr, nullptr};  // two dz buffers: gate-grad of step n+1 overlaps the wgrad of step n
   float* scale = nullptr;  // device {S, 1/S}
   unsigned int* amax = nullptr;
   CUtensorMap m_dz128, m_dz64, m_dzhalo;
+  CUtensorMap m_dz128b[2], m_dz64b[2], m_dzhalob[2];
+  cudaStream_t side = nullptr;                    // weight-gradient stream (created at bind)
+  cudaEvent_t ev_d[2] = {nullptr, nullptr};       // dgrad of the step using buffer i has been enqueued/finished
+  cudaEvent_t ev_w[2] = {nullptr, nullptr};       // wgrad has finished reading buffer i
+  cudaEvent_t ev_fork = nullptr;
   bool pair_ok = false;  // geometry allows the CTA-pair halo kernel (one-row 128-pixel tiles)
 };
 
@@ -718,16 +724,18 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
 // accumulation.  dh sources (fp32 NHWC, scaled by S) may be null.  c_prev may be null (zeros).
 template <typename E>
 int cell_gate_grad(const Ctx& ctx, CellState& cs, const void* gates, const float* c_prev, const float* c_next,
-                   const float* dh0, const float* dh1, const float* dh2, int first, cudaStream_t st) {
-  // pointwise gate gradient (backward of layers/ConvLSTM.py:48-55)
-  gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 33 * sizeof(float), st>>>(
-      static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dz), cs.bpart, !first,
-      ctx.geo.npix(), ctx.HP);
+                   const float* dh0, const float* dh1, const float* dh2, int first, cudaStream_t st, int buf = 0) {
+  // pointwise gate gradient (backward of layers/ConvLSTM.py:48-55).  (Forcing the max-shared-memory carveout so
+  // it could co-reside with a wgrad CTA slows it from 442 to 614 us — it needs L1 for its loads in flight — and the
+  // two kernels still did not overlap: DESIGN.md "backward overlap".)
+  gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 9 * sizeof(float), st>>>(
+      static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dzb[buf]), cs.bpart,
+      !first, ctx.geo.npix(), ctx.HP);
   return after_launch("gate_grad_kernel");
 }
 
 template <typename E>
-int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
+int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
   // d[x | h_prev] = conv_transpose(dz, W)  (backward of layers/ConvLSTM.py:45-47)
   const CellGeom& g = cs.g;
   ConvGemmParams p;
@@ -744,29 +752,30 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st) {
   p.out_scale = 1.f;
   {
     bool used = false;
-    RC_TRY((launch_dgradT<E>(ctx.dev, ctx.m_dz128, cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
+    RC_TRY((launch_dgradT<E>(ctx.dev, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
                              cs.rows_d, p.split_col, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
   if (ctx.pair_ok && env_int("CLSTM_HALO2_DGRAD", 0)) {
     bool used = false;
-    RC_TRY((launch_halo2<E, EPI_STORE>(ctx.dev, ctx.m_dzhalo, ctx.m_dzhalo, cs.m_wd32, cs.with_x ? cs.m_dx16 : cs.m_dh16,
+    RC_TRY((launch_halo2<E, EPI_STORE>(ctx.dev, ctx.m_dzhalob[buf], ctx.m_dzhalob[buf], cs.m_wd32, cs.with_x ? cs.m_dx16 : cs.m_dh16,
                                        cs.m_dh16, cs.m_dh16, p, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
   if (ctx.pair_ok) {
     bool used = false;
     const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
-    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, halo ? ctx.m_dzhalo : ctx.m_dz128, halo ? ctx.m_dzhalo : ctx.m_dz128,
+    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, halo ? ctx.m_dzhalob[buf] : ctx.m_dz128b[buf],
+                                          halo ? ctx.m_dzhalob[buf] : ctx.m_dz128b[buf],
                                           cs.m_wd_half, p, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
-  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128, ctx.m_dz128, cs.m_wd, p, ctx.geo, ctx.geo.B, st,
+  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128b[buf], ctx.m_dz128b[buf], cs.m_wd, p, ctx.geo, ctx.geo.B, st,
                                        cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16);
 }
 
 template <typename E>
-int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st) {
+int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st, int buf = 0) {
   // dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
   const CellGeom& g = cs.g;
   const Geo& geo = ctx.geo;
@@ -784,7 +793,7 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
   p.splits = cs.wg_splits;
   p.partial = cs.wpart;
   p.accumulate = !first;
-  return launch_wgrad<E>(ctx.dev, ctx.m_dz64, *in.map64, cs.m_h64, p, geo, geo.B, st);
+  return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st);
 }
 
 template <typename E>
@@ -871,7 +880,9 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   p->wh = cv.take<void>(static_cast<size_t>(p->NT) * 9 * HP * 2);
   p->bias_h = cv.take<float>(static_cast<size_t>(p->NT) * 4);
   if (c.training) {
-    ctx.dz = cv.take<void>(npix * 4 * HP * 2);
+    ctx.dzb[0] = cv.take<void>(npix * 4 * HP * 2);
+    ctx.dzb[1] = cv.take<void>(npix * 4 * HP * 2);
+    ctx.dz = ctx.dzb[0];
     p->G = cv.take<void>(npix * p->KG * 2);
     p->dstack = cv.take<float>(npix * HP * 4);
     p->whd = cv.take<void>(static_cast<size_t>(HP) * p->KG * 2);
@@ -1048,6 +1059,16 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     }
   }
 
+  // Backward schedule.  Per cell step: G = gate-grad (HBM bound) -> D = dgrad (tensor bound, on the critical
+  // chain) and W = wgrad (tensor bound, off the chain: only the final reduction needs it).  W runs on a side
+  // stream and is released when D has been issued, so W of step n executes concurrently with G of step n+1
+  // (the gate-grad kernel is small enough to co-reside with a wgrad CTA on every SM) — two dz buffers alternate.
+  const bool overlap = env_int("CLSTM_OVERLAP", 0) != 0 && ctx.side != nullptr;
+  int nstep = 0;
+  if (overlap) {
+    CU_TRY(cudaEventRecord(ctx.ev_fork, st));
+    CU_TRY(cudaStreamWaitEvent(ctx.side, ctx.ev_fork, 0));  // the side stream starts after everything enqueued so far
+  }
   auto back = [&](int k, int t, const float* e1, const float* e2) -> int {
     CellState& cs = p->cells[k];
     const InputRef in = plan_input(p, k, t);
@@ -1055,7 +1076,19 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
     const float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
     const float* own = (t == cs.T - 1) ? nullptr : cs.dh_own;
-    return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st);
+    if (!overlap) return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st);
+    const int buf = nstep & 1;
+    const int first = cs.bwd_started ? 0 : 1;
+    cs.bwd_started = true;
+    if (nstep >= 2) CU_TRY(cudaStreamWaitEvent(st, ctx.ev_w[buf], 0));  // wgrad n-2 has finished reading dz[buf]
+    RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, e1, e2, first, st, buf));
+    RC_TRY(cell_dgrad<E>(ctx, cs, st, buf));
+    CU_TRY(cudaEventRecord(ctx.ev_d[buf], st));
+    CU_TRY(cudaStreamWaitEvent(ctx.side, ctx.ev_d[buf], 0));
+    RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, t), first, ctx.side, buf));
+    CU_TRY(cudaEventRecord(ctx.ev_w[buf], ctx.side));
+    ++nstep;
+    return 0;
   };
 
   CellState& last = p->cells[ncell - 1];
@@ -1103,6 +1136,10 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   for (int t = c.t_in - 1; t >= 0; --t) {
     RC_TRY(back(L - 1, t, (t == c.t_in - 1) ? dfeed : nullptr, nullptr));
     for (int k = L - 2; k >= 0; --k) RC_TRY(back(k, t, p->cells[k + 1].dxb, nullptr));
+  }
+  if (overlap) {  // join: the partial sums of every wgrad are complete
+    CU_TRY(cudaEventRecord(ctx.ev_fork, ctx.side));
+    CU_TRY(cudaStreamWaitEvent(st, ctx.ev_fork, 0));
   }
   for (int k = 0; k < ncell; ++k) RC_TRY(cell_finalize(ctx, p->cells[k], grads[2 * k], grads[2 * k + 1], accumulate, st));
   if (grads[2 * ncell]) {
@@ -1164,6 +1201,7 @@ void carve_cell_plan(clstm_cell_plan* p, uint8_t* base) {
   p->xin = cv.take<void>(npix * p->cs.g.CIP * 2);
   carve_cell(cv, p->cs, ctx);
   ctx.dz = cv.take<void>(npix * 4 * ctx.HP * 2);
+  ctx.dzb[0] = ctx.dzb[1] = ctx.dz;
   p->ws_bytes = align_up(cv.off, 1024);
 }
 
@@ -1337,6 +1375,15 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
 }
 
 int clstm_plan_destroy(clstm_plan_t* plan) {
+  if (plan && plan->ctx.side) {
+    cudaStreamSynchronize(plan->ctx.side);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(plan->ctx.ev_d[i]);
+      cudaEventDestroy(plan->ctx.ev_w[i]);
+    }
+    cudaEventDestroy(plan->ctx.ev_fork);
+    cudaStreamDestroy(plan->ctx.side);
+  }
   delete plan;
   return 0;
 }
@@ -1376,8 +1423,23 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   if (c.training) {
     RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
-    if (ctx.pair_ok)
+    for (int i = 0; i < 2; ++i) {
+      RC_TRY(make_map_act(&ctx.m_dz128b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
+      RC_TRY(make_map_act(&ctx.m_dz64b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
+    }
+    if (!ctx.side) {
+      CU_TRY(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&ctx.ev_d[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ctx.ev_w[i], cudaEventDisableTiming));
+      }
+      CU_TRY(cudaEventCreateWithFlags(&ctx.ev_fork, cudaEventDisableTiming));
+    }
+    if (ctx.pair_ok) {
       RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
+      for (int i = 0; i < 2; ++i)
+        RC_TRY(make_map_act(&ctx.m_dzhalob[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
+    }
     RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
     RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd / weight_boxes(p->n_tile_hd)));
@@ -1481,6 +1543,21 @@ int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, voi
       return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
     }
+    case 4: {  // experiment: weight-gradient on the side stream concurrently with a gate-gradient on `stream`
+      Ctx& cx = p->ctx;
+      if (!cx.side) return fail(CLSTM_ESTATE, "no side stream");
+      CU_TRY(cudaEventRecord(cx.ev_fork, st));
+      CU_TRY(cudaStreamWaitEvent(cx.side, cx.ev_fork, 0));
+#define CALL_(E) cell_wgrad<E>(p->ctx, cs, in, hslot(cs, step), 0, cx.side, 1)
+      RC_TRY(DISPATCH_E(p->cfg.dtype, CALL_));
+#undef CALL_
+#define CALL_(E) cell_gate_grad<E>(p->ctx, cs, gates, c_prev, c_next, cs.dh_own, p->dstack, nullptr, 0, st, 0)
+      RC_TRY(DISPATCH_E(p->cfg.dtype, CALL_));
+#undef CALL_
+      CU_TRY(cudaEventRecord(cx.ev_w[0], cx.side));
+      CU_TRY(cudaStreamWaitEvent(st, cx.ev_w[0], 0));
+      return 0;
+    }
     default:
       return fail(CLSTM_EINVAL, "unknown kernel kind %d", kind);
   }
@@ -1536,8 +1613,10 @@ int clstm_cell_plan_bind(clstm_cell_plan_t* p, void* workspace, size_t bytes, vo
   RC_TRY(make_map_act(&p->m_x64, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, g.BW2, g.BH2));
   RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
   RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW2, g.BH2));
+  for (int i = 0; i < 2; ++i) ctx.m_dz128b[i] = ctx.m_dz128, ctx.m_dz64b[i] = ctx.m_dz64;
   if (ctx.pair_ok) {
     RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
+    ctx.m_dzhalob[0] = ctx.m_dzhalob[1] = ctx.m_dzhalo;
     RC_TRY(make_map_act(&p->m_xhalo, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
   }
   p->bound = true;

@@ -343,7 +343,7 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
                  const float* __restrict__ dh0, const float* __restrict__ dh1, const float* __restrict__ dh2,
                  float* __restrict__ dc, E* __restrict__ dz, float* __restrict__ bias_partial, int bias_accumulate,
                  size_t npix, int HP) {
-  extern __shared__ float red[];  // [256][33] padded
+  extern __shared__ float red[];  // [256][9] padded
   const int groups = HP / 8;
   const int grp = threadIdx.x % groups;
   const int plane = threadIdx.x / groups;
@@ -422,21 +422,24 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
                      Elem<E>::pack2(dzv[a][4], dzv[a][5]), Elem<E>::pack2(dzv[a][6], dzv[a][7]));
     }
   }
-  // block reduction of the bias partial sums over the `ppb` pixel lanes (fixed order -> deterministic)
-  float* mine = red + threadIdx.x * 33;
+  // block reduction of the bias partial sums over the `ppb` pixel lanes (fixed order -> deterministic), one
+  // gate at a time so the kernel needs only 256 x 9 floats of shared memory: it must be able to co-reside with
+  // a weight-gradient CTA (198 KB of shared memory) on the same SM (DESIGN.md "backward overlap").
+#pragma unroll 1
+  for (int a = 0; a < 4; ++a) {
+    float* mine = red + threadIdx.x * 9;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) mine[a * 8 + e] = bsum[a][e];
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    for (int v = 0; v < 32; ++v) {
-      float s = 0.f;
-      for (int pl = 0; pl < ppb; ++pl) s += red[(pl * groups + threadIdx.x) * 33 + v];
-      const int a = v / 8, e = v % 8;
-      float* dst = bias_partial + static_cast<size_t>(blockIdx.x) * 4 * HP + a * HP + threadIdx.x * 8 + e;
-      *dst = bias_accumulate ? *dst + s : s;
+    for (int e = 0; e < 8; ++e) mine[e] = bsum[a][e];
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      for (int e = 0; e < 8; ++e) {
+        float s = 0.f;
+        for (int pl = 0; pl < ppb; ++pl) s += red[(pl * groups + threadIdx.x) * 9 + e];
+        float* dst = bias_partial + static_cast<size_t>(blockIdx.x) * 4 * HP + a * HP + threadIdx.x * 8 + e;
+        *dst = bias_accumulate ? *dst + s : s;
+      }
     }
+    __syncthreads();
   }
 }
 
