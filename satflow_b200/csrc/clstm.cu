@@ -274,6 +274,7 @@ struct CellState {
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
   CUtensorMap m_h128, m_h64, m_hhalo, m_hhalo3, m_wp, m_wd, m_wp_half, m_wd_half;
   CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
+  CUtensorMap m_h66;                                // wgrad halo rows: box 64 ch x 66 px x 1 row
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue
   std::vector<CUtensorMap> m_c16s, m_h16s, m_g16s;   // the same, one map per slot / step (N = B images, offset 0)
@@ -286,6 +287,7 @@ struct CellState {
 struct InputRef {
   const CUtensorMap* map128 = nullptr;
   const CUtensorMap* map64 = nullptr;
+  const CUtensorMap* map66 = nullptr;    // wgrad halo rows (conv inputs only)
   const CUtensorMap* maphalo = nullptr;  // one-row halo boxes (pair kernel); == map128 for direct inputs
   int b_off = 0;  // image offset (slot * B)
 };
@@ -359,6 +361,7 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   const long long imgs = static_cast<long long>(cs.slots_h) * g.B;
   RC_TRY(make_map_act(&cs.m_h128, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
   RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
+  if (g.BW2 == 64 && g.BH2 == 1) RC_TRY(make_map_act(&cs.m_h66, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 66, 1));
   RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256 / weight_boxes(256)));
   if (ctx.training)
     RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / weight_boxes(cs.n_tile_d)));
@@ -599,13 +602,13 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW2, p.BH = g.BH2, p.tiles_w = g.tiles_w2, p.tiles_h = g.tiles_h2;
   p.num_p_tiles = static_cast<int>(images) * g.tiles_w2 * g.tiles_h2;
-  const int stage_bytes = (2 + p.group_size) * kWgTileP * 128;
+  const int stage_bytes = p.halo ? (2 * kWgTileP * 128 + 2 * kWgHaloRowBytes) : (2 + p.group_size) * kWgTileP * 128;
   int stages = (dev.smem_optin - static_cast<int>(wgrad_smem_bytes(0, 0))) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(CLSTM_EINVAL, "wgrad: not enough shared memory");
   p.stages = stages;
   p.dbg_no_tma = env_int("CLSTM_WG_NOTMA", 0);
-  const size_t smem = wgrad_smem_bytes(stages, p.group_size);
+  const size_t smem = wgrad_smem_bytes(0, 0) + static_cast<size_t>(stages) * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
@@ -793,6 +796,12 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
   p.splits = cs.wg_splits;
   p.partial = cs.wpart;
   p.accumulate = !first;
+  // halo rows: both segments 3x3 convs over one 64-channel chunk, 64-pixel single-row K steps, groups of 6 taps
+  if (!g.in_col && g.kh == 3 && g.kw == 3 && g.CIP == 64 && ctx.HP == 64 && geo.BW2 == 64 && geo.BH2 == 1 &&
+      cs.wg_group == 6 && cs.wg_total == 18 && in.map66 != nullptr && env_int("CLSTM_WG_HALO", 1)) {
+    p.halo = 1;
+    return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st);
+  }
   return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st);
 }
 
@@ -924,10 +933,11 @@ InputRef plan_input(clstm_plan* p, int k, int t) {
     // decoder_1 input: encoder_vector (:185, :189) = last encoder h at t == 0, else last decoder h (:195)
     const CellState& src = (t == 0) ? p->cells[L - 1] : p->cells[p->ncell - 1];
     const int s = (t == 0) ? hslot(src, p->cfg.t_in) : hslot(src, t);
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.maphalo = &src.m_hhalo, in.b_off = s * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.maphalo = &src.m_hhalo, in.b_off = s * B;
   } else {
     const CellState& src = p->cells[k - 1];  // the layer below, already stepped to t + 1 (:180, :192)
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.maphalo = &src.m_hhalo, in.b_off = hslot(src, t + 1) * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.maphalo = &src.m_hhalo,
+    in.b_off = hslot(src, t + 1) * B;
   }
   return in;
 }

@@ -19,6 +19,7 @@ namespace clstm {
 constexpr int kWgTileP = 64;  // pixels per K step
 constexpr int kWgMaxGroupBlocks = 8;
 constexpr int kWgThreads = 256;
+constexpr int kWgHaloRowBytes = 9216;  // one halo row slot: 66 pixels x 128 B, padded to a multiple of 1024
 
 // Column blocks of one operand tensor: block j -> tap j / chunks (row-major over (kh, kw)), 64-channel
 // chunk j % chunks.  A "direct" segment has kw == 1, cy == cx == 0 and a single tap.
@@ -43,6 +44,7 @@ struct WgradParams {
   int stages;
   float* partial;  // [splits][n_blocks*128][total_blocks*64] fp32
   int accumulate;  // 0: overwrite, 1: +=
+  int halo;        // 1: 3x3 taps served from halo rows (see wgrad_kernel); requires chunks == 1, BW == 64, BH == 1
   int dbg_no_tma;  // experiment: after the first ring fill, reuse shared memory (no TMA) -> pure MMA rate
 };
 
@@ -62,7 +64,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int nblk = min(p.group_size, p.total_blocks - blk0);
 
   constexpr int kBoxBytes = kWgTileP * 128;  // one 64-channel x 64-pixel box
-  const int stage_bytes = (2 + nblk) * kBoxBytes;
+  // halo mode: a group is two filter rows (6 taps) = two [66 px x 64 ch] halo rows instead of six 64-pixel boxes;
+  // the three horizontal taps of a row are ONE N = 192 MMA whose 64-channel groups are LBO = 128 B (one pixel)
+  // apart, i.e. overlapping views of the same row shifted by one pixel each.
+  const int stage_bytes = p.halo ? (2 * kBoxBytes + 2 * kWgHaloRowBytes) : (2 + nblk) * kBoxBytes;
   uint8_t* tail = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + 8;
@@ -95,7 +100,40 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // Lanes 0 .. nblk+1 each own one box of the stage (lane 0/1: the two A boxes, lane 2+j: column block j), so
     // the boxes of a stage are issued in parallel instead of serially by one thread.
-    if (lane < 2 + nblk) {
+    if (p.halo) {
+      if (lane < 4) {
+        // lanes 0,1: the two A boxes; lanes 2,3: halo rows rho = 2*grp + (lane-2): segment rho/3, filter row rho%3
+        const CUtensorMap* map = &tmA;
+        int c0 = nb * 128 + lane * 64, dxs = 0, dys = 0, boff = p.a_b_off;
+        uint32_t bytes_off = lane * kBoxBytes;
+        if (lane >= 2) {
+          const int rho = 2 * grp + (lane - 2);
+          const int sidx = rho / 3;
+          map = sidx == 0 ? &tmB0 : &tmB1;
+          c0 = 0;
+          dxs = -1;
+          dys = rho % 3 - 1;
+          boff = p.seg[sidx].b_off;
+          bytes_off = 2 * kBoxBytes + (lane - 2) * kWgHaloRowBytes;
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+          const int pt = split + it * p.splits;
+          const int tw = pt % p.tiles_w;
+          const int th = (pt / p.tiles_w) % p.tiles_h;
+          const int b = pt / (p.tiles_w * p.tiles_h);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) mbar_expect_tx(&full_bar[stage], 2 * kBoxBytes + 2 * 66 * 128);
+          tma_load_4d(smem + stage * stage_bytes + bytes_off, map, &full_bar[stage], c0, tw * p.BW + dxs, th * p.BH + dys,
+                      b + boff);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (lane < 2 + nblk) {
       // per-lane constants of the box this lane loads
       const CUtensorMap* map = &tmA;
       int c0 = nb * 128 + lane * 64, dxs = 0, dys = 0, boff = p.a_b_off;
@@ -145,6 +183,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tcgen05_fence_after();
         const uint32_t base = smem_u32(smem + stage * stage_bytes);
         const uint64_t adesc = make_smem_desc_sw128(base, kBoxBytes, 1024);
+        if (p.halo) {
+          const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 192, 1, 1);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint64_t bdesc = make_smem_desc_sw128(base + 2 * kBoxBytes + r * kWgHaloRowBytes, 128, 1024);
+#pragma unroll
+            for (int k = 0; k < kWgTileP / 16; ++k)
+              umma_f16(tmem_base + r * 192, adesc + k * 128, bdesc + k * 128, idesc, (it | k) != 0);
+          }
+        } else
         for (int j = 0; j < nblk; j += 4) {
           const int nb4 = min(4, nblk - j);
           const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 64 * nb4, 1, 1);
