@@ -238,6 +238,8 @@ struct Ctx {
   unsigned int* amax = nullptr;
   CUtensorMap m_dz128, m_dz64, m_dzhalo;
   CUtensorMap m_dz128b[2], m_dz64b[2], m_dzhalob[2];
+  CUtensorMap m_dzrow256[2], m_dzrow8[2];  // halo-row dgradT: 256-pixel and 8-pixel single-row boxes
+  bool rows_ok = false;
   cudaStream_t side = nullptr;                    // weight-gradient stream (created at bind)
   cudaEvent_t ev_d[2] = {nullptr, nullptr};       // dgrad of the step using buffer i has been enqueued/finished
   cudaEvent_t ev_w[2] = {nullptr, nullptr};       // wgrad has finished reading buffer i
@@ -596,6 +598,37 @@ int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtenso
   return after_launch("dgradT_kernel");
 }
 
+// Halo-row transposed dgrad (3x3, W > 128).
+template <typename E>
+int launch_dgradT_halo(const DeviceInfo& dev, const CUtensorMap& row256, const CUtensorMap& row8, const CUtensorMap& wT,
+                       const CUtensorMap& x0, const CUtensorMap& x1, const ConvSeg& seg, int rows_d, int split_col,
+                       const Geo& g, cudaStream_t st, bool* used) {
+  *used = false;
+  if (seg.kh != 3 || seg.kw != 3 || g.W <= 128 || !env_int("CLSTM_DGRADT_HALO", 0)) return 0;
+  DgradTHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = g.B, p.H = g.H, p.W = g.W;
+  p.segs_w = (g.W + 255) / 256;
+  p.chunks = seg.chunks;
+  p.m_tiles = (rows_d + 127) / 128;
+  p.split_col = split_col;
+  p.rows = 4;
+  p.w_stages = 4;
+  while (p.w_stages < kMaxStages && dgradTh_smem_bytes(p.w_stages + 1, p.rows) <= static_cast<size_t>(dev.smem_optin))
+    ++p.w_stages;
+  if (dgradTh_smem_bytes(p.w_stages, p.rows) > static_cast<size_t>(dev.smem_optin)) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(dgradT_halo_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  const long long units = static_cast<long long>(g.B) * g.H * p.segs_w * p.m_tiles;
+  const int grid = units < dev.sms ? static_cast<int>(units) : dev.sms;
+  dgradT_halo_kernel<E><<<grid, kGemmThreads, dgradTh_smem_bytes(p.w_stages, p.rows), st>>>(row256, row8, wT, x0, x1, p);
+  *used = true;
+  return after_launch("dgradT_halo_kernel");
+}
+
 template <typename E>
 int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
                  WgradParams p, const Geo& g, long long images, cudaStream_t st) {
@@ -753,6 +786,13 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
   p.ld0 = g.CIP;
   p.ld1 = ctx.HP;
   p.out_scale = 1.f;
+  if (ctx.rows_ok) {
+    bool used = false;
+    RC_TRY((launch_dgradT_halo<E>(ctx.dev, ctx.m_dzrow256[buf], ctx.m_dzrow8[buf], cs.m_wdT,
+                                  cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0], cs.rows_d, p.split_col, ctx.geo, st,
+                                  &used)));
+    if (used) return 0;
+  }
   {
     bool used = false;
     RC_TRY((launch_dgradT<E>(ctx.dev, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
@@ -1436,6 +1476,11 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     for (int i = 0; i < 2; ++i) {
       RC_TRY(make_map_act(&ctx.m_dz128b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
       RC_TRY(make_map_act(&ctx.m_dz64b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
+      if (g.W > 128) {
+        RC_TRY(make_map_act(&ctx.m_dzrow256[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 256, 1));
+        RC_TRY(make_map_act(&ctx.m_dzrow8[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 8, 1));
+        ctx.rows_ok = true;
+      }
     }
     if (!ctx.side) {
       CU_TRY(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
