@@ -193,8 +193,7 @@ def run_ours(args):
 
     def train_step(x, tgt):
         bucket.zero_()
-        y_hat = model(x, t_out).permute(0, 2, 1, 3, 4)  # conv_lstm.py:55-56
-        loss = model.criterion(y_hat, tgt)  # conv_lstm.py:63 (MSE)
+        loss = model.training_step((x, tgt), 0)  # conv_lstm.py:53-70: forward, MSE loss, per-frame losses
         loss.backward()
         bucket.all_reduce_mean()
         opt.step()

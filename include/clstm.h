@@ -133,6 +133,14 @@ int clstm_cell_forward(clstm_cell_plan_t* plan, const float* x, const float* h_c
 int clstm_cell_backward(clstm_cell_plan_t* plan, const float* dh_next, const float* dc_next, const float* weight,
                         float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, void* stream);
 
+/* ---- fused MSE loss + gradient (EncoderDecoderConvLSTM.training_step, conv_lstm.py:55-69) --------------------
+ * y (B,C,T,H,W) = the rollout output, target (B,T,C,H,W) as the reference's batches; writes
+ *   out[0] = mean((permute(y) - target)^2), out[1 + t] = the same mean over frame t (the reference's per-frame
+ *   losses, one .item() host sync each at :66-69), dy (B,C,T,H,W) = d out[0] / d y (may be NULL).
+ * partial: device scratch of B*T*C floats.  Two-stage ordered reduction: bit-reproducible. */
+int clstm_mse_loss_grad(const float* y, const float* target, int batch, int channels, int t_out, int height, int width,
+                        float* dy, float* partial, float* out, void* stream);
+
 /* Number of kernels this library has launched since load (all plans, this process). */
 uint64_t clstm_launch_count(void);
 

@@ -9,5 +9,6 @@ from .registry import create_model, get_model, is_model, list_models, register_m
 from .layers import ConvLSTMCell, get_conv_layer  # noqa: F401
 from .conv_lstm import ConvLSTM, EncoderDecoderConvLSTM, get_loss  # noqa: F401
 from .plan import CellPlan, RolloutPlan  # noqa: F401
+from .loss import fused_mse  # noqa: F401
 
 __version__ = "0.1.0"

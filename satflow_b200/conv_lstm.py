@@ -216,13 +216,25 @@ class EncoderDecoderConvLSTM(_Base):
             vals = per.tolist()
         return {f"{prefix}/frame_{f}_loss": v for f, v in enumerate(vals)}
 
+    def loss_and_frame_losses(self, out, y):
+        """out: forward output (B, C, T, H, W); y: target (B, T, C, H, W).  MSE (the reference default) runs as one
+        fused kernel producing loss, gradient and the per-frame losses of conv_lstm.py:66-69 without host syncs."""
+        if isinstance(self.criterion, nn.MSELoss) and out.is_cuda and self.criterion.reduction == "mean":
+            from .loss import fused_mse
+
+            return fused_mse(out, y)
+        y_hat = torch.permute(out, dims=(0, 2, 1, 3, 4))  # conv_lstm.py:56
+        loss = self.criterion(y_hat, y)
+        with torch.no_grad():
+            frames = torch.stack([self.criterion(y_hat[:, f], y[:, f]) for f in range(y_hat.shape[1])])
+        return loss, frames
+
     def training_step(self, batch, batch_idx):
         x, y = batch
-        y_hat = self(x, self.forecast_steps)
-        y_hat = torch.permute(y_hat, dims=(0, 2, 1, 3, 4))  # conv_lstm.py:56
-        loss = self.criterion(y_hat, y)
+        out = self(x, self.forecast_steps)
+        loss, frames = self.loss_and_frame_losses(out, y)
         self.log("train/loss", loss, on_step=True)
-        self.log_dict(self._frame_losses(y_hat, y, "train"))
+        self.frame_losses = frames.detach()  # device tensor; fetch with one .tolist() when needed
         return loss
 
     def validation_step(self, batch, batch_idx):

@@ -1699,6 +1699,25 @@ int clstm_cell_backward(clstm_cell_plan_t* p, const float* dh_next, const float*
 #undef CALL_
 }
 
+// ---------------------------------------------------------------------------- fused loss
+int clstm_mse_loss_grad(const float* y, const float* target, int batch, int channels, int t_out, int height, int width,
+                        float* dy, float* partial, float* out, void* stream) {
+  if (!y || !target || !partial || !out) return fail(CLSTM_EINVAL, "null argument");
+  if (batch < 1 || channels < 1 || t_out < 1 || t_out > 1024 || height < 1 || width < 1)
+    return fail(CLSTM_EINVAL, "bad shape (t_out must be <= 1024)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long planes = static_cast<long long>(batch) * t_out * channels;
+  if (planes > 0x7fffffffll) return fail(CLSTM_EINVAL, "too many planes");
+  const int hw = height * width;
+  const double n = static_cast<double>(planes) * hw;
+  mse_loss_grad_kernel<<<static_cast<int>(planes), 256, 0, st>>>(y, target, dy, partial, batch, channels, t_out, hw,
+                                                                  static_cast<float>(2.0 / n));
+  RC_TRY(after_launch("mse_loss_grad_kernel"));
+  mse_finalize_kernel<<<1, 1024, 0, st>>>(partial, out, batch, channels, t_out, static_cast<float>(1.0 / n),
+                                          static_cast<float>(static_cast<double>(t_out) / n));
+  return after_launch("mse_finalize_kernel");
+}
+
 // ---------------------------------------------------------------------------- bring-up experiments
 int clstm_selftest_shifted_desc(float* out_max_abs_err, int n_variants, int n_shifts, void* stream) {
   if (!out_max_abs_err || n_variants < 1 || n_shifts < 1) return fail(CLSTM_EINVAL, "bad argument");

@@ -605,6 +605,73 @@ head_grad_amax_kernel(const float* __restrict__ dyv, const float* __restrict__ y
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused MSE loss + gradient (training_step, conv_lstm.py:55-69): y is the rollout output (B,C,T,H,W), target is
+// (B,T,C,H,W) as the reference's batches are; one block per (b, t, c) plane (contiguous in both tensors).
+//   partial[(b*T + t)*C + c] = sum over the plane of (y - target)^2        (ordered -> deterministic)
+//   dy = (2 / N) * (y - target)   in y's layout, N = B*C*T*H*W
+// mse_finalize_kernel turns the partials into the mean loss and the T per-frame means (the reference fetches each
+// of those with its own .item() host sync, conv_lstm.py:66-69).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mse_loss_grad_kernel(const float* __restrict__ y, const float* __restrict__ target, float* __restrict__ dy,
+                     float* __restrict__ partial, int B, int C, int T, int HW, float two_over_n) {
+  int idx = blockIdx.x;
+  const int c = idx % C;
+  idx /= C;
+  const int t = idx % T;
+  const int b = idx / T;
+  const size_t yo = ((static_cast<size_t>(b) * C + c) * T + t) * HW;
+  const size_t to = ((static_cast<size_t>(b) * T + t) * C + c) * HW;
+  float s = 0.f;
+  if ((HW & 3) == 0) {
+    const float4* y4 = reinterpret_cast<const float4*>(y + yo);
+    const float4* t4 = reinterpret_cast<const float4*>(target + to);
+    float4* d4 = dy ? reinterpret_cast<float4*>(dy + yo) : nullptr;
+    for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
+      const float4 a = __ldg(y4 + i), g = __ldg(t4 + i);
+      const float4 d = make_float4(a.x - g.x, a.y - g.y, a.z - g.z, a.w - g.w);
+      s += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+      if (d4) d4[i] = make_float4(d.x * two_over_n, d.y * two_over_n, d.z * two_over_n, d.w * two_over_n);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float d = __ldg(y + yo + i) - __ldg(target + to + i);
+      s += d * d;
+      if (dy) dy[yo + i] = d * two_over_n;
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// out[0] = mean loss, out[1 + t] = mean loss of frame t
+__global__ void mse_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int B, int C, int T,
+                                    float inv_n_total, float inv_n_frame) {
+  const int t = threadIdx.x;
+  __shared__ float frame[1024];
+  float s = 0.f;
+  if (t < T)
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < C; ++c) s += partial[(static_cast<size_t>(b) * T + t) * C + c];
+  if (t < T) {
+    frame[t] = s;
+    out[1 + t] = s * inv_n_frame;
+  }
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < T; ++i) tot += frame[i];
+    out[0] = tot * inv_n_total;
+  }
+}
+
 // amax_bits <- max(amax_bits, max |a|)
 __global__ void __launch_bounds__(256)
 abs_amax_kernel(const float* __restrict__ a, size_t n, unsigned int* __restrict__ amax_bits) {
