@@ -92,6 +92,12 @@ int clstm_plan_set_weights(clstm_plan_t* plan, const float* const* params, int n
 /* ConvLSTM.forward (conv_lstm.py:205-228): x (B,T_in,C,H,W) fp32 -> y (B,C_out,T_out,H,W) fp32. */
 int clstm_rollout_forward(clstm_plan_t* plan, const float* x, float* y, void* stream);
 
+/* The same with an explicit input layout: CLSTM_X_BTHWC is the channels-last (B,T_in,H,W,C) layout that the
+ * reference's datasets emit (satflow/data/datasets.py:70-106, data/datamodules.py:188-219), consumed without a
+ * permute copy. */
+enum { CLSTM_X_BTCHW = 0, CLSTM_X_BTHWC = 1 };
+int clstm_rollout_forward_layout(clstm_plan_t* plan, const float* x, int x_layout, float* y, void* stream);
+
 /* Backward of clstm_rollout_forward (what loss.backward() does to conv_lstm.py:171-203):
  * dy, y are (B,C_out,T_out,H,W) fp32 (y = the forward output); grads has the same order and
  * shapes as `params`; accumulate != 0 adds into grads (like autograd's .grad +=), 0 overwrites.

@@ -54,6 +54,7 @@ _PROTOTYPES = {
     "clstm_plan_bind": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "clstm_plan_set_weights": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p]),
     "clstm_rollout_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "clstm_rollout_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "clstm_rollout_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p]),
     "clstm_plan_read_state": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "clstm_plan_profile_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),

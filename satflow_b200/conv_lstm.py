@@ -64,9 +64,9 @@ class _RolloutFn(torch.autograd.Function):
     """One autograd node for the whole encoder-forecaster rollout (not one per cell)."""
 
     @staticmethod
-    def forward(ctx, plan: RolloutPlan, x: torch.Tensor, *params: torch.Tensor):
+    def forward(ctx, plan: RolloutPlan, x: torch.Tensor, channels_last: bool, *params: torch.Tensor):
         plan.set_weights(params)
-        y = plan.forward(x)
+        y = plan.forward(x, channels_last=channels_last)
         ctx.plan = plan
         ctx.n_params = len(params)
         ctx.save_for_backward(y, *params)
@@ -76,9 +76,9 @@ class _RolloutFn(torch.autograd.Function):
     def backward(ctx, dy):
         y = ctx.saved_tensors[0]
         params = ctx.saved_tensors[1:]
-        grads = [torch.empty_like(p) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(params)]
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[3 + i] else None for i, p in enumerate(params)]
         ctx.plan.backward(dy, y, grads, accumulate=False)
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 class ConvLSTM(nn.Module):
@@ -122,8 +122,11 @@ class ConvLSTM(nn.Module):
         out += [self.decoder_CNN.weight, self.decoder_CNN.bias]
         return out
 
-    def plan_for(self, x: torch.Tensor, forecast_steps: int, training: bool) -> RolloutPlan:
-        b, seq_len, c, h, w = x.shape
+    def plan_for(self, x: torch.Tensor, forecast_steps: int, training: bool, channels_last: bool = False) -> RolloutPlan:
+        if channels_last:
+            b, seq_len, h, w, c = x.shape
+        else:
+            b, seq_len, c, h, w = x.shape
         key = (b, seq_len, c, h, w, forecast_steps, training, self.operand_dtype, x.device.index)
         plan = self._plans.get(key)
         if plan is None:
@@ -142,13 +145,18 @@ class ConvLSTM(nn.Module):
         self._plans.clear()
 
     # ---- reference API ----------------------------------------------------------------------
-    def forward(self, x, forecast_steps=0, hidden_state=None):
+    def forward_channels_last(self, x, forecast_steps=0):
+        """The same rollout on a channels-last batch (B, T_in, H, W, C) — the layout the reference's datasets emit
+        (data/datasets.py:70-106) — consumed without a permute copy."""
+        return self.forward(x, forecast_steps, channels_last=True)
+
+    def forward(self, x, forecast_steps=0, hidden_state=None, channels_last: bool = False):
         """x: (B, T_in, C, H, W) float32 CUDA -> (B, out_channels, T_out, H, W)   (conv_lstm.py:205-228).
         ``hidden_state`` is accepted and ignored exactly like the reference (:205 never reads it)."""
         if x.dim() != 5:
             raise RuntimeError(f"ConvLSTM expects a 5-D (b, t, c, h, w) tensor, got {tuple(x.shape)}")
-        if x.shape[2] != self.input_channels:
-            raise RuntimeError(f"expected {self.input_channels} input channels, got {x.shape[2]}")
+        if x.shape[4 if channels_last else 2] != self.input_channels:
+            raise RuntimeError(f"expected {self.input_channels} input channels, got {x.shape[4 if channels_last else 2]}")
         if forecast_steps <= 0:
             # the reference reaches torch.stack([]) at conv_lstm.py:198
             raise RuntimeError("stack expects a non-empty TensorList")
@@ -159,10 +167,10 @@ class ConvLSTM(nn.Module):
             )
         params = self.rollout_params()
         training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        plan = self.plan_for(x, int(forecast_steps), training)
+        plan = self.plan_for(x, int(forecast_steps), training, channels_last)
         if x.dtype != torch.float32:
             x = x.float()
-        return _RolloutFn.apply(plan, x, *params)
+        return _RolloutFn.apply(plan, x, bool(channels_last), *params)
 
 
 @register_model
@@ -198,6 +206,25 @@ class EncoderDecoderConvLSTM(_Base):
             forecast_steps=config.get("forecast_steps", 1),
             lr=config.get("lr", 0.001),
         )
+
+    @classmethod
+    def from_yaml(cls, path):
+        """Build from a Hydra model YAML of the reference's shape (configs/model/convlstm.yaml: ``_target_`` plus
+        constructor kwargs); unknown keys are rejected like a wrong kwarg would be."""
+        import yaml
+
+        with open(path) as f:
+            cfg = yaml.safe_load(f) or {}
+        cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
+        return cls(**cfg)
+
+    def load_lightning_checkpoint(self, ckpt, strict: bool = True):
+        """Load a reference Lightning checkpoint (path or dict): ``state_dict`` has the keys of SURVEY.md §8(b);
+        ``hyper_parameters`` (from save_hyperparameters, conv_lstm.py:33) are returned for inspection."""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location="cpu")
+        self.load_state_dict(ckpt.get("state_dict", ckpt), strict=strict)
+        return ckpt.get("hyper_parameters", {})
 
     def forward(self, x, future_seq=0, hidden_state=None):
         return self.model.forward(x, future_seq, hidden_state)

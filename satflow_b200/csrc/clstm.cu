@@ -999,7 +999,7 @@ int plan_set_weights(clstm_plan* p, const float* const* params, cudaStream_t st)
 }
 
 template <typename E>
-int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
+int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int channels_last = 0) {
   const clstm_config_t& c = p->cfg;
   const Ctx& ctx = p->ctx;
   const Geo& geo = ctx.geo;
@@ -1008,11 +1008,15 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st) {
   const int L = p->L;
   // x (B,T,C,H,W) -> im2col'd 16-bit tensor, once for all T_in steps
   bool tiled = false;
-  RC_TRY((launch_row_im2col<E, 0>(x, nullptr, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels, c.height,
-                                  c.width, c.kernel_h, c.kernel_w, p->KX, 0, c.t_in, nullptr, st, &tiled)));
+  if (channels_last)
+    RC_TRY((launch_row_im2col<E, 2>(x, nullptr, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels, c.height,
+                                    c.width, c.kernel_h, c.kernel_w, p->KX, 0, c.t_in, nullptr, st, &tiled)));
+  else
+    RC_TRY((launch_row_im2col<E, 0>(x, nullptr, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels, c.height,
+                                    c.width, c.kernel_h, c.kernel_w, p->KX, 0, c.t_in, nullptr, st, &tiled)));
   if (!tiled) {
     pack_xcol_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xcol), c.batch, c.t_in, c.in_channels,
-                                                     c.height, c.width, c.kernel_h, c.kernel_w, p->KX);
+                                                     c.height, c.width, c.kernel_h, c.kernel_w, p->KX, channels_last);
     RC_TRY(after_launch("pack_xcol_kernel"));
   }
   if (!c.training) {
@@ -1522,10 +1526,15 @@ int clstm_plan_set_weights(clstm_plan_t* p, const float* const* params, int n_pa
 }
 
 int clstm_rollout_forward(clstm_plan_t* p, const float* x, float* y, void* stream) {
+  return clstm_rollout_forward_layout(p, x, CLSTM_X_BTCHW, y, stream);
+}
+
+int clstm_rollout_forward_layout(clstm_plan_t* p, const float* x, int x_layout, float* y, void* stream) {
   if (!p || !x || !y) return fail(CLSTM_EINVAL, "null argument");
   if (!p->bound || !p->weights_set) return fail(CLSTM_ESTATE, "forward before bind / set_weights");
+  if (x_layout != CLSTM_X_BTCHW && x_layout != CLSTM_X_BTHWC) return fail(CLSTM_EINVAL, "unknown x layout %d", x_layout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL_(E) plan_forward<E>(p, x, y, st)
+#define CALL_(E) plan_forward<E>(p, x, y, st, x_layout == CLSTM_X_BTHWC)
   return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
 }

@@ -13,7 +13,7 @@ namespace clstm {
 // ------------------------------------------------------------------------------------------
 template <typename E>
 __global__ void pack_xcol_kernel(const float* __restrict__ x, E* __restrict__ xcol, int B, int T, int C, int H,
-                                 int W, int kh, int kw, int KX) {
+                                 int W, int kh, int kw, int KX, int channels_last = 0) {
   const int chunks = KX / 8;
   const size_t total = static_cast<size_t>(T) * B * H * W * chunks;
   const int kreal = kh * kw * C;
@@ -36,7 +36,8 @@ __global__ void pack_xcol_kernel(const float* __restrict__ x, E* __restrict__ xc
         const int tap = k / C, c = k % C;
         const int hy = h + tap / kw - kh / 2, wx = w + tap % kw - kw / 2;
         if (hy >= 0 && hy < H && wx >= 0 && wx < W)
-          val = __ldg(x + (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W + wx);
+          val = channels_last ? __ldg(x + ((((static_cast<size_t>(b) * T + t) * H + hy) * W + wx) * C + c))
+                              : __ldg(x + (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W + wx);
       }
       v[e] = val;
     }
@@ -74,8 +75,8 @@ row_im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1
     if (k < kh * kw * C) {
       const int tap = k / C, c = k % C;
       const int dyi = tap / kw, dxi = tap % kw;
-      const int r = (MODE == 0) ? dyi : kh - 1 - dyi;
-      const int col = (MODE == 0) ? dxi : kw - 1 - dxi;
+      const int r = (MODE != 1) ? dyi : kh - 1 - dyi;
+      const int col = (MODE != 1) ? dxi : kw - 1 - dxi;
       off = (r * C + c) * WP + col;
     }
     lut[k] = off;
@@ -90,6 +91,15 @@ row_im2col_kernel(const float* __restrict__ src0, const float* __restrict__ src1
     E* dst = sm + static_cast<size_t>(ln) * WP;
     if (hy < 0 || hy >= H) {
       for (int wcol = lane; wcol < WP; wcol += 32) dst[wcol] = Elem<E>::from_float(0.f);
+      continue;
+    }
+    if (MODE == 2) {  // channels-last source (B,T,H,W,C): the reference datasets' on-wire layout (data/datasets.py:70-106)
+      const size_t rowbase = (((static_cast<size_t>(b) * T + t) * H + hy) * W) * C + c;
+#pragma unroll 4
+      for (int wcol = lane; wcol < WP; wcol += 32) {
+        const int wx = wcol - kw / 2;
+        dst[wcol] = Elem<E>::from_float((wx >= 0 && wx < W) ? __ldg(src0 + rowbase + static_cast<size_t>(wx) * C) : 0.f);
+      }
       continue;
     }
     const size_t base = (MODE == 0) ? (((static_cast<size_t>(b) * T + t) * C + c) * H + hy) * W

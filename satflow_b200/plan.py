@@ -101,16 +101,22 @@ class RolloutPlan:
             )
         self._weights_key = key
 
-    def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, channels_last: bool = False) -> torch.Tensor:
         c = self.cfg
         _require_cuda(x, "x")
-        if tuple(x.shape) != (c.batch, c.t_in, c.in_channels, c.height, c.width):
-            raise ValueError(f"x has shape {tuple(x.shape)}, plan expects {(c.batch, c.t_in, c.in_channels, c.height, c.width)}")
+        want = ((c.batch, c.t_in, c.height, c.width, c.in_channels) if channels_last
+                else (c.batch, c.t_in, c.in_channels, c.height, c.width))
+        if tuple(x.shape) != want:
+            raise ValueError(f"x has shape {tuple(x.shape)}, plan expects {want}")
         x = x.contiguous()
         if y is None:
             y = torch.empty(c.batch, c.out_channels, c.t_out, c.height, c.width, dtype=torch.float32, device=x.device)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().clstm_rollout_forward(self._h, _lib.ptr(x), _lib.ptr(y), _stream_ptr(self.device)))
+            _lib.check(
+                _lib.lib().clstm_rollout_forward_layout(
+                    self._h, _lib.ptr(x), 1 if channels_last else 0, _lib.ptr(y), _stream_ptr(self.device)
+                )
+            )
         return y
 
     def backward(self, dy: torch.Tensor, y: torch.Tensor, grads: Sequence[Optional[torch.Tensor]], accumulate: bool = False):

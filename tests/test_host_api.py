@@ -122,3 +122,20 @@ def test_state_dict_layout_matches_reference_fixture():
     assert h.shape == (2, 16, 5, 7) and float(h.abs().sum() + c.abs().sum()) == 0.0
     # CloudGAN's init_net matches sub-modules whose class name contains "Conv" and that own .weight (gan/common.py:46-64)
     assert "Conv" in type(cell.conv).__name__ and hasattr(cell.conv, "weight")
+
+
+def test_yaml_and_lightning_checkpoint_helpers(tmp_path):
+    # configs/model/convlstm.yaml has exactly these keys (reference defaults: 17 channels, forecast 24, lr 1e-4)
+    y = tmp_path / "convlstm.yaml"
+    y.write_text("# @package _group_\n_target_: satflow.models.conv_lstm.EncoderDecoderConvLSTM\ninput_channels: 17\n"
+                 "hidden_dim: 64\nout_channels: 1\nforecast_steps: 24\nlr: 0.0001\nvisualize: True\n")
+    m = S.EncoderDecoderConvLSTM.from_yaml(str(y))
+    assert (m.model.input_channels, m.model.hidden_dim, m.forecast_steps, m.lr, m.visualize) == (17, 64, 24, 0.0001, True)
+    z = load_golden("rollout_h16_12x10")
+    sd = {k[len("param."):]: v for k, v in z.items() if k.startswith("param.")}
+    ck = tmp_path / "best.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": {"hidden_dim": 16, "forecast_steps": 4}}, ck)
+    m2 = S.EncoderDecoderConvLSTM(hidden_dim=16, input_channels=12, out_channels=5, forecast_steps=4)
+    hp = m2.load_lightning_checkpoint(str(ck))
+    assert hp["hidden_dim"] == 16
+    assert torch.equal(m2.state_dict()["model.decoder_CNN.bias"], sd["model.decoder_CNN.bias"])
