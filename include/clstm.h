@@ -118,7 +118,9 @@ enum {
   CLSTM_KERNEL_CELL_FWD = 0,  /* fused conv + LSTM epilogue (layers/ConvLSTM.py:45-55) */
   CLSTM_KERNEL_GATE_GRAD = 1, /* pointwise gate gradient */
   CLSTM_KERNEL_DGRAD = 2,     /* data gradient GEMM */
-  CLSTM_KERNEL_WGRAD = 3      /* weight gradient GEMM */
+  CLSTM_KERNEL_WGRAD = 3,     /* weight gradient GEMM */
+  CLSTM_KERNEL_DGRAD_FUSED = 5 /* data gradient GEMM of (cell, step) whose epilogue also runs the gate gradient of
+                                  cell-1 at the same step (the default backward schedule; needs cell >= 1) */
 };
 int clstm_plan_profile_kernel(clstm_plan_t* plan, int kind, int cell, int step, void* stream);
 

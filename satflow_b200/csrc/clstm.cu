@@ -602,6 +602,38 @@ int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtenso
   return after_launch("dgradT_kernel");
 }
 
+// Transposed dgrad whose epilogue also runs the gate gradient of the NEXT cell step of the backward chain.
+template <typename E>
+int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x1,
+                        const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f, cudaStream_t st) {
+  DgradTParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
+  p.seg = seg;
+  p.m_tiles = 1;
+  p.lbw = 0;
+  while ((1 << p.lbw) < g.BW) ++p.lbw;
+  int stages = (dev.smem_optin - static_cast<int>(dgradTf_smem_bytes(0))) / kDtStageBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return fail(CLSTM_EINVAL, "dgradT_fused: not enough shared memory");
+  p.stages = stages;
+  const int units = (p.num_m_tiles + 1) / 2;
+  const int grid = units < dev.sms ? units : dev.sms;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  if (env_int("CLSTM_FUSE_TEAMS", 2) == 4)
+    dgradT_fused_kernel<E, 4><<<grid, 128 + 4 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
+  else
+    dgradT_fused_kernel<E, 2><<<grid, 128 + 2 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
+  return after_launch("dgradT_fused_kernel");
+}
+
 // Halo-row transposed dgrad (3x3, W > 128).
 template <typename E>
 int launch_dgradT_halo(const DeviceInfo& dev, const CUtensorMap& row256, const CUtensorMap& row8, const CUtensorMap& wT,
@@ -821,6 +853,47 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
                                        cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16);
 }
 
+// slot of a cell's h / c state after `s` steps (s = 0: initial zeros); see pick_stride for the permutation
+inline int hslot(const CellState& cs, int s) { return ((s % cs.slots_h) * cs.h_stride + cs.h_rot) % cs.slots_h; }
+inline int cslot(const CellState& cs, int s) { return (s % cs.slots_c) * cs.c_stride % cs.slots_c; }
+
+// dgrad of `cs` (reading dz[buf]) with the gate gradient of the NEXT step of the backward chain — cell `cn`, time
+// step `nt`, dh sources own / e1 / e2 — fused into its epilogue (dgradT.cuh); that gate gradient lands in dz[buf^1].
+// A source equal to cs.dxb is the dx this launch produces: it is consumed from shared memory and never written.
+template <typename E>
+int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const float* own, const float* e1,
+                     const float* e2, int buf, cudaStream_t st) {
+  const size_t npix = ctx.geo.npix();
+  const int HP = ctx.HP;
+  GateFuse f;
+  memset(&f, 0, sizeof(f));
+  f.gates = static_cast<const E*>(cn.gates) + static_cast<size_t>(nt) * npix * 4 * HP;
+  f.c_prev = (nt == 0) ? nullptr : cn.c + static_cast<size_t>(cslot(cn, nt)) * npix * HP;
+  f.c_next = cn.c + static_cast<size_t>(cslot(cn, nt + 1)) * npix * HP;
+  const float* srcs[3] = {own, e1, e2};
+  for (const float*& sp : srcs)
+    if (sp != nullptr && cs.with_x && sp == cs.dxb) {
+      f.use_stg = 1;
+      sp = nullptr;
+    }
+  f.src0 = srcs[0], f.src1 = srcs[1], f.src2 = srcs[2];
+  f.h_block = cs.with_x ? 1 : 0;
+  f.dc = cn.dc;
+  f.dz_out = ctx.dzb[buf ^ 1];
+  f.bias_partial = cn.bpart;
+  f.HP = HP;
+  f.pf_dist = env_int("CLSTM_FUSE_PF", 1);
+  return launch_dgradT_fused<E>(ctx.dev, ctx.m_dz128b[buf], cs.m_wdT, cs.m_dhT, ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0},
+                                ctx.geo, ctx.geo.B, f, st);
+}
+
+// Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
+inline bool fuse_supported(const Ctx& ctx) {
+  const bool halo_dgrad = ctx.rows_ok && env_int("CLSTM_DGRADT_HALO", 0);
+  return !halo_dgrad && ctx.HP == 64 && ctx.geo.BW >= 16 && ctx.geo.npix() * 4 * ctx.HP < (1ull << 32) &&
+         env_int("CLSTM_DGRADT", 1) && env_int("CLSTM_FUSE_GATE", 1);
+}
+
 template <typename E>
 int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st, int buf = 0) {
   // dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
@@ -945,13 +1018,10 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   p->ws_bytes = align_up(cv.off, 1024);
 }
 
-// slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
-// Memory slot of a state after `s` steps.  Full stacks are PERMUTED: consecutive time steps live
+// Full state stacks are PERMUTED (hslot / cslot above): consecutive time steps live
 // slot_stride slots apart (mod the slot count).  Measured on B200 (DESIGN.md §4 "slot placement"): a cell step
 // that reads h slot m while writing h slot m +- 1 (128 MB away) loses ~100 us to the write stream; 3 slots
 // apart costs ~15 us.
-inline int hslot(const CellState& cs, int s) { return ((s % cs.slots_h) * cs.h_stride + cs.h_rot) % cs.slots_h; }
-inline int cslot(const CellState& cs, int s) { return (s % cs.slots_c) * cs.c_stride % cs.slots_c; }
 inline int pick_stride(int slots, int want) {
   if (slots <= 3 || want <= 1) return 1;
   auto gcd = [](int a, int b) {
@@ -1150,9 +1220,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   };
 
   CellState& last = p->cells[ncell - 1];
-  const float* dfeed = nullptr;  // grad wrt the decoder input of step t + 1
-  for (int t = c.t_out - 1; t >= 0; --t) {
-    // head backward for this output frame: dlogit "col" tensor -> dgrad into dstack, wgrad accumulation
+  // head backward for output frame t: dlogit "col" tensor -> dgrad into dstack, wgrad accumulation
+  auto head_back = [&](int t) -> int {
     bool tiled = false;
     RC_TRY((launch_row_im2col<E, 1>(dy, y, static_cast<E*>(p->G), c.batch, c.t_out, c.out_channels, c.height, c.width,
                                     3, 3, p->KG, t, 1, ctx.scale, st, &tiled)));
@@ -1187,13 +1256,71 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       wp.accumulate = (t != c.t_out - 1);
       RC_TRY((launch_wgrad<E>(ctx.dev, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st)));
     }
-    RC_TRY(back(ncell - 1, t, p->dstack, dfeed));
-    for (int k = ncell - 2; k >= L; --k) RC_TRY(back(k, t, p->cells[k + 1].dxb, nullptr));
-    dfeed = p->cells[L].dxb;
+    return 0;
+  };
+
+  // The chain of cell steps in backward order (conv_lstm.py:176-196 reversed); e1 / e2 = the dh sources besides the
+  // cell's own recurrent dh: the head (dstack), the cell above (its dx) and the decoder feedback (dx of cell L).
+  struct BackOp {
+    int k, t;
+    const float *e1, *e2;
+    bool head;  // the head backward of frame t must have run before this step's gate gradient
+  };
+  std::vector<BackOp> ops;
+  ops.reserve(static_cast<size_t>(L) * (c.t_in + c.t_out));
+  for (int t = c.t_out - 1; t >= 0; --t) {
+    ops.push_back({ncell - 1, t, p->dstack, (t == c.t_out - 1) ? nullptr : p->cells[L].dxb, true});
+    for (int k = ncell - 2; k >= L; --k) ops.push_back({k, t, p->cells[k + 1].dxb, nullptr, false});
   }
   for (int t = c.t_in - 1; t >= 0; --t) {
-    RC_TRY(back(L - 1, t, (t == c.t_in - 1) ? dfeed : nullptr, nullptr));
-    for (int k = L - 2; k >= 0; --k) RC_TRY(back(k, t, p->cells[k + 1].dxb, nullptr));
+    ops.push_back({L - 1, t, (t == c.t_in - 1) ? p->cells[L].dxb : nullptr, nullptr, false});
+    for (int k = L - 2; k >= 0; --k) ops.push_back({k, t, p->cells[k + 1].dxb, nullptr, false});
+  }
+
+  // Fused schedule: the gate gradient of step n+1 runs inside the epilogue of dgrad n (dgradT.cuh) whenever the shapes
+  // allow, so the HBM-bound pointwise pass overlaps the tensor-bound GEMM.  dz alternates between two buffers
+  // (dgrad n reads dz[b] through TMA while its epilogue writes dz[b^1]).
+  const bool fuse = !overlap && L >= 2 && fuse_supported(ctx);
+  if (fuse) {
+    for (int k = 0; k < ncell; ++k)
+      CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0, static_cast<size_t>(kGateGradBlocks) * 4 * HP * 4, st));
+    int b = 0;
+    bool gate_done = false;  // gate gradient of ops[n] already computed into dz[b] by the previous dgrad
+    for (size_t n = 0; n < ops.size(); ++n) {
+      const BackOp& o = ops[n];
+      CellState& cs = p->cells[o.k];
+      const InputRef in = plan_input(p, o.k, o.t);
+      const int first = cs.bwd_started ? 0 : 1;
+      cs.bwd_started = true;
+      if (!gate_done) {
+        if (o.head) RC_TRY(head_back(o.t));
+        const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(o.t) * npix * 4 * HP;
+        const float* c_prev = (o.t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, o.t)) * npix * HP;
+        const float* c_next = cs.c + static_cast<size_t>(cslot(cs, o.t + 1)) * npix * HP;
+        const float* own = (o.t == cs.T - 1) ? nullptr : cs.dh_own;
+        RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b));
+      }
+      gate_done = false;
+      bool fused_here = false;
+      if (n + 1 < ops.size() && (!cs.with_x || cs.g.CIP == 64)) {
+        const BackOp& nx = ops[n + 1];
+        CellState& cn = p->cells[nx.k];
+        if (nx.k != o.k) {
+          if (nx.head) RC_TRY(head_back(nx.t));  // dstack must be ready; nothing in flight still reads it
+          RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, (nx.t == cn.T - 1) ? nullptr : cn.dh_own, nx.e1, nx.e2, b, st));
+          fused_here = true;
+          gate_done = true;
+        }
+      }
+      if (!fused_here) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b));
+      if (fused_here) b ^= 1;
+    }
+  } else {
+    for (const BackOp& o : ops) {
+      if (o.head) RC_TRY(head_back(o.t));
+      RC_TRY(back(o.k, o.t, o.e1, o.e2));
+    }
   }
   if (overlap) {  // join: the partial sums of every wgrad are complete
     CU_TRY(cudaEventRecord(ctx.ev_fork, ctx.side));
@@ -1625,6 +1752,15 @@ int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, voi
       CU_TRY(cudaEventRecord(cx.ev_w[0], cx.side));
       CU_TRY(cudaStreamWaitEvent(st, cx.ev_w[0], 0));
       return 0;
+    }
+    case CLSTM_KERNEL_DGRAD_FUSED: {  // dgrad of (cell, step) + gate gradient of the cell below at the same step
+      if (cell < 1 || !cs.with_x || cs.g.CIP != 64 || !fuse_supported(p->ctx))
+        return fail(CLSTM_EINVAL, "fused dgrad + gate-gradient is not available for this cell / shape");
+      CellState& cn = p->cells[cell - 1];
+      if (step >= cn.T) return fail(CLSTM_EINVAL, "step %d out of range for the consumer cell", step);
+#define CALL_(E) cell_dgrad_fused<E>(p->ctx, cs, cn, step, cn.dh_own, cs.dxb, nullptr, 0, st)
+      return DISPATCH_E(p->cfg.dtype, CALL_);
+#undef CALL_
     }
     default:
       return fail(CLSTM_EINVAL, "unknown kernel kind %d", kind);

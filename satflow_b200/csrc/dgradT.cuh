@@ -206,6 +206,381 @@ dgradT_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ 
 }  // namespace clstm
 
 // ======================================================================================================
+// dgradT with the NEXT gate-gradient fused into its epilogue.
+//
+// In BPTT the x-part of dgrad(cell k+1, step t) is the last-arriving gradient source of gate-grad(cell k, step t)
+// (likewise the decoder feedback).  gate-grad is a pure HBM stream (2.4 GB, 0.43 ms) during which the tensor
+// pipes idle, and dgradT is tensor bound with DRAM 25 % busy — so the epilogue of dgradT consumes its own x-part
+// tile straight from shared memory and runs the gate-gradient math of the consumer cell for those pixels:
+// it adds the consumer's other dh sources, reads gates / c_prev / c_next / dc, writes dz (16-bit, into the OTHER dz
+// buffer — this kernel is still reading its own dz through TMA), updates dc in place and accumulates the bias
+// partial sums.  dx is never written or re-read, the separate gate-grad launch disappears, and its memory traffic
+// overlaps the MMAs.  Pixel groups are 32 wide; thread mapping of the fused part = gate_grad_kernel's
+// (one pixel x 8 channels per item).
+// ======================================================================================================
+namespace clstm {
+
+constexpr int kDfStgHalf = 16384;  // [2 blocks (x|h)][32 px][64 ch] fp32
+
+struct GateFuse {
+  const void* gates;     // E [pix][4*HP] of the consumer cell / step
+  const float* c_prev;   // nullable (zeros)
+  const float* c_next;
+  const float* src0;     // dh sources of the consumer read from global memory (nullable), fp32 [pix][HP], scaled by S
+  const float* src1;
+  const float* src2;
+  int use_stg;           // 1: staging block 0 (this launch's dx tile, 64 channels) is one more dh source
+  int h_block;           // staging block holding dh_prev of the producing cell (1 with an x part, else 0)
+  int pf_dist;           // L2 prefetch distance in 32-pixel groups (0 = off)
+  float* dc;             // in/out
+  void* dz_out;          // E [pix][4*HP]
+  float* bias_partial;   // [gridDim.x][4*HP], accumulated
+  int HP;
+};
+
+inline size_t dgradTf_smem_bytes(int stages) {
+  return 1024 + static_cast<size_t>(stages) * kDtStageBytes + 2 * kDfStgHalf + (2 * kMaxStages + 4) * 8 + 16 + 64;
+}
+
+// TEAMS = epilogue teams of 4 warps (one warp per TMEM lane quadrant); a team owns 256/TEAMS accumulator columns.
+// TEAMS = 2: 384 threads, 32-pixel groups, two register sets of loads in flight per thread.
+// TEAMS = 4: 640 threads (<= 96 registers), 16-pixel groups, one set per thread — twice the warps per scheduler.
+template <typename E, int TEAMS>
+__global__ void __launch_bounds__(128 + TEAMS * 128, 1)
+dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmX1, const DgradTParams p, const GateFuse f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_stg = smem + p.stages * kDtStageBytes;
+  uint8_t* tail = smem_stg + 2 * kDfStgHalf;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = (p.num_m_tiles + 1) >> 1;  // m_tiles == 1: 64 x-channels + 64 h-channels
+  const int taps = p.seg.kh * p.seg.kw;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDz);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * TEAMS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int GP = 64 / TEAMS;          // pixels per epilogue group
+  constexpr int TCOLS = 256 / TEAMS;      // accumulator columns (pixels) per team
+  constexpr int STG_TEAM = 2 * GP * 64;   // floats of staging per team: [2 blocks (x|h)][GP px][64 ch]
+
+  auto tile_origin = [&](int unit, int t, int& w0, int& h0, int& b) {
+    const int mt = 2 * unit + t;
+    w0 = (mt % p.tiles_w) * p.BW;
+    h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
+    b = mt / (p.tiles_w * p.tiles_h);
+  };
+
+  if (warp == 0) {
+    if (lane < 3) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int w0 = 0, h0 = 0, b = 0;
+        if (lane > 0) tile_origin(unit, lane - 1, w0, h0, b);
+        int kb = 0;
+        for (int dy = 0; dy < p.seg.kh; ++dy)
+          for (int dx = 0; dx < p.seg.kw; ++dx)
+            for (int ch = 0; ch < p.seg.chunks; ++ch, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* dst = smem + stage * kDtStageBytes;
+              if (lane == 0) {
+                mbar_expect_tx(&full_bar[stage], kDtStageBytes);
+                tma_load_2d(dst, &tmW, &full_bar[stage], kb * kBlockK, 0);
+              } else {
+                tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmDz, &full_bar[stage], ch * kBlockK,
+                            w0 + dx - p.seg.kw / 2, h0 + dy - p.seg.kh / 2, b + p.seg.b_off);
+              }
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 256, 0, 0);
+      const int kblocks = taps * p.seg.chunks;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t base = smem_u32(smem + stage * kDtStageBytes);
+          const uint64_t adesc = make_smem_desc_sw128(base, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(base + 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: transpose 32-pixel groups, h-part -> TMA store, x-part -> fused gate-grad ======
+    // The gate-gradient part is latency bound unless its global loads are kept in flight while the thread drains
+    // TMEM and waits at barriers: items are 1 pixel x 4 channels (32 registers of raw loads), two register sets
+    // ping-pong, and the loads of an item are issued two items ahead — across group and unit boundaries.
+    const int q = warp & 3;
+    const int team = (warp - 4) >> 2;
+    const int half = team / (TEAMS / 2);          // pixel tile of the unit
+    const int pcol0 = (team % (TEAMS / 2)) * TCOLS;  // first tile pixel of this team
+    const int cl = q * 32 + lane;                 // channel within the 128 output rows == thread inside the team
+    float* stg = reinterpret_cast<float*>(smem_stg) + team * STG_TEAM;  // [2][GP px][64 ch]
+    const int bar_id = 1 + team;
+    const int HP = f.HP;
+    const int chunk = cl & 15;                    // 4-channel chunk of the consumer's hidden channels
+    const int pxl = cl >> 4;                      // 0..7: pixel inside an 8-pixel pass
+    const E* gates = static_cast<const E*>(f.gates);
+    E* dzo = static_cast<E*>(f.dz_out);
+    float bsum[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+
+    struct Raw {
+      uint2 g[4];
+      float4 cp, cn, dc, s0, s1, s2;
+      unsigned pix;  // global pixel index (B*H*W < 2^32 / (4*HP) is checked on the host)
+      bool valid;
+    };
+    // Per-unit tile base (integer divisions once per unit, not per item): first pixel index of this half's pixel
+    // tile, and the number of valid rows / columns inside it (0 rows = padding tile or no such unit).
+    struct TileBase {
+      unsigned pix0;
+      int rows, cols;
+    };
+    auto tile_base = [&](int unit) -> TileBase {
+      TileBase t{0u, 0, 0};
+      if (unit >= total_units) return t;
+      int w0, h0, b;
+      tile_origin(unit, half, w0, h0, b);
+      if (b >= p.B) return t;
+      t.pix0 = (static_cast<unsigned>(b) * p.H + h0) * p.W + w0;
+      t.rows = p.H - h0;
+      t.cols = p.W - w0;
+      return t;
+    };
+    // thread-constant bases (the chunk offset folded in)
+    const E* gates_c = gates + chunk * 4;
+    E* dzo_c = dzo + chunk * 4;
+    const float* cp_c = f.c_prev ? f.c_prev + chunk * 4 : nullptr;
+    const float* cn_c = f.c_next + chunk * 4;
+    float* dc_c = f.dc + chunk * 4;
+    const float* s0_c = f.src0 ? f.src0 + chunk * 4 : nullptr;
+    const float* s1_c = f.src1 ? f.src1 + chunk * 4 : nullptr;
+    const float* s2_c = f.src2 ? f.src2 + chunk * 4 : nullptr;
+    const int bwm = p.BW - 1;
+
+    auto issue = [&](Raw& r, const TileBase& tb, int g, int s) {
+      const int px = pcol0 + g * GP + s * 8 + pxl;
+      const int lx = px & bwm, ly = px >> p.lbw;
+      r.valid = ly < tb.rows && lx < tb.cols;
+      if (!r.valid) return;
+      r.pix = tb.pix0 + ly * p.W + lx;
+      const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;  // HP == 64
+      r.g[0] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4));
+      r.g[1] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 64));
+      r.g[2] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 128));
+      r.g[3] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 192));
+      r.cp = cp_c ? __ldg(reinterpret_cast<const float4*>(cp_c + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r.cn = __ldg(reinterpret_cast<const float4*>(cn_c + o1));
+      r.dc = *reinterpret_cast<const float4*>(dc_c + o1);  // read and written by this thread only
+      if (s0_c) r.s0 = __ldg(reinterpret_cast<const float4*>(s0_c + o1));
+      if (s1_c) r.s1 = __ldg(reinterpret_cast<const float4*>(s1_c + o1));
+      if (s2_c) r.s2 = __ldg(reinterpret_cast<const float4*>(s2_c + o1));
+    };
+    const float* stg_c = stg + pxl * 64 + chunk * 4;
+    auto consume = [&](const Raw& r, int s) {
+      if (!r.valid) return;
+      float dhv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (f.use_stg) {
+        const float4 a0 = *reinterpret_cast<const float4*>(stg_c + s * (8 * 64));
+        dhv[0] = a0.x, dhv[1] = a0.y, dhv[2] = a0.z, dhv[3] = a0.w;
+      }
+      if (s0_c) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
+      if (s1_c) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
+      if (s2_c) dhv[0] += r.s2.x, dhv[1] += r.s2.y, dhv[2] += r.s2.z, dhv[3] += r.s2.w;
+      float gv[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float2 p0 = Elem<E>::unpack2(r.g[a].x), p1 = Elem<E>::unpack2(r.g[a].y);
+        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+      }
+      const float cp[4] = {r.cp.x, r.cp.y, r.cp.z, r.cp.w};
+      const float cn[4] = {r.cn.x, r.cn.y, r.cn.z, r.cn.w};
+      const float dcv[4] = {r.dc.x, r.dc.y, r.dc.z, r.dc.w};
+      float dzv[4][4], dcn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
+        const float tc = fast_tanh(cn[e]);
+        const float d_o = dhv[e] * tc;
+        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
+        dzv[0][e] = dct * gg * gi * (1.f - gi);
+        dzv[1][e] = dct * cp[e] * gf * (1.f - gf);
+        dzv[2][e] = d_o * go * (1.f - go);
+        dzv[3][e] = dct * gi * (1.f - gg * gg);
+        dcn[e] = dct * gf;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
+      }
+      const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;
+      *reinterpret_cast<float4*>(dc_c + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
+            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+    };
+
+    // L2 prefetch of the lines the NEXT group will load (costs no registers: the memory system holds the requests).
+    // Thread -> (pixel = cl / 4, quarter = cl % 4): one gate line (64 ch x 2 B) and every 4th fp32 half-row line.
+    auto prefetch_group = [&](const TileBase& tb, int g) {
+      if ((cl >> 2) >= GP) return;
+      const int px = pcol0 + g * GP + (cl >> 2), sub = cl & 3;
+      const int lx = px & bwm, ly = px >> p.lbw;
+      if (ly >= tb.rows || lx >= tb.cols) return;
+      const unsigned pix = tb.pix0 + ly * p.W + lx;
+      prefetch_l2(gates + pix * (4 * 64) + sub * 64);
+      const float* arr[6] = {f.c_prev, f.c_next, f.dc, f.src0, f.src1, f.src2};
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+          if (((j * 2 + l) & 3) == sub && arr[j] != nullptr) prefetch_l2(arr[j] + pix * 64 + l * 32);
+    };
+
+    TileBase tb_cur = tile_base(blockIdx.x), tb_next;
+    Raw ra, rb;
+    issue(ra, tb_cur, 0, 0);
+    if (TEAMS == 2) issue(rb, tb_cur, 0, 1);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      int w0, h0, b;
+      tile_origin(unit, half, w0, h0, b);
+      tb_next = tile_base(unit + static_cast<int>(gridDim.x));
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + team * TCOLS + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        {
+          uint32_t v[GP];
+#pragma unroll
+          for (int i = 0; i < GP / 16; ++i) tmem_ld16(taddr + g * GP + i * 16, *reinterpret_cast<uint32_t(*)[16]>(v + i * 16));
+          if (q == 0 && lane == 1) tma_store_wait_read();
+          named_bar_sync(bar_id, 128);  // staging free: the previous group's TMA store and fused reads are done
+          tmem_ld_wait();
+          if (g == 3) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          float* dst = stg + (cl >> 6) * (GP * 64) + (cl & 63);
+#pragma unroll
+          for (int j = 0; j < GP; ++j) dst[j * 64] = __uint_as_float(v[j]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (q == 0 && lane == 1) {  // dh_prev of this cell (64 channels), 16-pixel boxes
+#pragma unroll
+          for (int s2 = 0; s2 < GP / 16; ++s2) {
+            const int px = pcol0 + g * GP + s2 * 16;
+            tma_store_4d(&tmX1, stg + f.h_block * (GP * 64) + s2 * 16 * 64, 0, w0 + (px & (p.BW - 1)), h0 + (px >> p.lbw),
+                         b);
+          }
+          tma_store_commit();
+        }
+        // fused gate gradient of the consumer cell: passes of 8 pixels, loads issued ahead of their use
+        const int ng = (g + 1) & 3;
+        const TileBase& tbn = (g == 3) ? tb_next : tb_cur;
+        if (f.pf_dist) prefetch_group(tbn, ng);
+        if (TEAMS == 2) {
+          consume(ra, 0);
+          issue(ra, tb_cur, g, 2);
+          consume(rb, 1);
+          issue(rb, tb_cur, g, 3);
+          consume(ra, 2);
+          issue(ra, tbn, ng, 0);
+          consume(rb, 3);
+          issue(rb, tbn, ng, 1);
+        } else {
+          consume(ra, 0);
+          issue(ra, tb_cur, g, 1);
+          consume(ra, 1);
+          issue(ra, tbn, ng, 0);
+        }
+      }
+      tb_cur = tb_next;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (q == 0 && lane == 1) tma_store_wait_all();
+    // bias partial sums: reduce over the 16 threads (both halves) that share a channel chunk, one gate at a time
+    const int te = threadIdx.x - 128;  // over the epilogue warps; te & 15 == chunk
+    float* red = reinterpret_cast<float*>(smem_stg);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {  // unrolled: bsum must stay in registers
+      named_bar_sync(1 + TEAMS, TEAMS * 128);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[te * 5 + e] = bsum[a][e];
+      named_bar_sync(1 + TEAMS, TEAMS * 128);
+      if (te < 16) {
+        for (int e = 0; e < 4; ++e) {
+          float sum = 0.f;
+          for (int pl = 0; pl < TEAMS * 8; ++pl) sum += red[(pl * 16 + te) * 5 + e];
+          f.bias_partial[static_cast<size_t>(blockIdx.x) * 4 * HP + a * HP + te * 4 + e] += sum;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace clstm
+
+// ======================================================================================================
 // Halo-row variant of the transposed dgrad (3x3 filters, W > 128): a unit is 256 consecutive pixels of ONE image
 // row.  For each 64-channel chunk of dz the three image rows h-1, h, h+1 are loaded once as [258 px x 64 ch] rows
 // (a 256-pixel box plus an 8-pixel box) into a ring of row slots; tap (dy, dx) is the B descriptor of row dy

@@ -435,8 +435,8 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
   // block reduction of the bias partial sums over the `ppb` pixel lanes (fixed order -> deterministic), one
   // gate at a time so the kernel needs only 256 x 9 floats of shared memory: it must be able to co-reside with
   // a weight-gradient CTA (198 KB of shared memory) on the same SM (DESIGN.md "backward overlap").
-#pragma unroll 1
-  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {  // unrolled so that bsum stays in registers
     float* mine = red + threadIdx.x * 9;
 #pragma unroll
     for (int e = 0; e < 8; ++e) mine[e] = bsum[a][e];

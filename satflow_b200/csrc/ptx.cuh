@@ -298,4 +298,8 @@ struct Elem<__nv_bfloat16> {
   __device__ static __forceinline__ float to_float(__nv_bfloat16 a) { return __bfloat162float(a); }
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 }  // namespace clstm

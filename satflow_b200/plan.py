@@ -130,7 +130,7 @@ class RolloutPlan:
                 )
             )
 
-    KERNELS = {"cell_fwd": 0, "gate_grad": 1, "dgrad": 2, "wgrad": 3, "wgrad+gate_grad": 4}
+    KERNELS = {"cell_fwd": 0, "gate_grad": 1, "dgrad": 2, "wgrad": 3, "wgrad+gate_grad": 4, "dgrad_fused": 5}
 
     def profile_kernel(self, kind: str, cell: int, step: int) -> None:
         """Re-launch one kernel of (cell, step) (measurement hook, include/clstm.h clstm_plan_profile_kernel)."""
