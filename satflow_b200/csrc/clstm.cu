@@ -22,6 +22,7 @@
 #include "convgemm2.cuh"
 #include "convgemm3.cuh"
 #include "dgradT.cuh"
+#include "head_rows.cuh"
 #include "pointwise.cuh"
 #include "selftest.cuh"
 #include "wgrad.cuh"
@@ -634,6 +635,51 @@ int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const C
   return after_launch("dgradT_fused_kernel");
 }
 
+// Row-marching output head (head_rows.cuh).  `used` stays false when the shape is not supported (the caller then
+// runs the implicit-GEMM head).
+template <typename E>
+int launch_head_rows(const DeviceInfo& dev, const CUtensorMap& h128, const CUtensorMap& wz, HeadRowsParams p,
+                     const Geo& g, cudaStream_t st, bool* used) {
+  *used = false;
+  if (g.BW != 128 || g.BH != 1 || p.c_out > 16 || !env_int("CLSTM_HEAD_ROWS", 1)) return 0;
+  p.H = g.H, p.W = g.W;
+  if (g.W <= 256) {
+    p.strips = 1, p.strip_w = 256, p.x_halo = 0;
+  } else {
+    p.strip_w = 254, p.x_halo = 1, p.strips = (g.W + 253) / 254;
+  }
+  p.band_rows = env_int("CLSTM_HEAD_BAND", 32);
+  p.bands = (g.H + p.band_rows - 1) / p.band_rows;
+  int stages = (dev.smem_optin - static_cast<int>(head_rows_smem_bytes(p.chunks, 0))) / kABytes;
+  if (stages > kHrMaxStages) stages = kHrMaxStages;
+  if (stages < 3) return 0;
+  p.stages = stages;
+  const long long units = static_cast<long long>(p.images) * p.strips * p.bands;
+  const int grid = units < dev.sms ? static_cast<int>(units) : dev.sms;
+  const size_t smem = head_rows_smem_bytes(p.chunks, stages);
+#define HR_LAUNCH(CO)                                                                                              \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      CU_TRY(cudaFuncSetAttribute(head_rows_kernel<E, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                  dev.smem_optin));                                                                \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    head_rows_kernel<E, CO><<<grid, kGemmThreads, smem, st>>>(h128, wz, p);                                        \
+  } while (0)
+  if (p.c_out <= 4)
+    HR_LAUNCH(4);
+  else if (p.c_out <= 8)
+    HR_LAUNCH(8);
+  else if (p.c_out <= 12)
+    HR_LAUNCH(12);
+  else
+    HR_LAUNCH(16);
+#undef HR_LAUNCH
+  *used = true;
+  return after_launch("head_rows_kernel");
+}
+
 // Halo-row transposed dgrad (3x3, W > 128).
 template <typename E>
 int launch_dgradT_halo(const DeviceInfo& dev, const CUtensorMap& row256, const CUtensorMap& row8, const CUtensorMap& wT,
@@ -982,12 +1028,13 @@ struct clstm_plan {
   void* G = nullptr;          // E [npix][KG]
   float* dstack = nullptr;    // fp32 [npix][HP]
   void* wh = nullptr;         // E [NT][9HP]
+  void* wz = nullptr;         // E [HP/64][144][64]: taps as output columns (head_rows.cuh); null if c_out > 16
   float* bias_h = nullptr;    // fp32 [NT]
   void* whd = nullptr;        // E [n_tile_hd rows = HP][KG]
   float* hpart = nullptr;     // fp32 [splits][128*(KG/128)][HP]
   float* hbpart = nullptr;    // fp32 [C_out][kHeadBiasChunks]
   int head_splits = 0, head_group = 0, n_tile_hd = 0;
-  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16;
+  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16, m_wz;
 };
 
 namespace {
@@ -1005,6 +1052,7 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   for (int k = 0; k < p->ncell; ++k) carve_cell(cv, p->cells[k], ctx);
   p->wh = cv.take<void>(static_cast<size_t>(p->NT) * 9 * HP * 2);
   p->bias_h = cv.take<float>(static_cast<size_t>(p->NT) * 4);
+  p->wz = (c.out_channels <= 16) ? cv.take<void>(static_cast<size_t>(HP / 64) * kHrN * 64 * 2) : nullptr;
   if (c.training) {
     ctx.dzb[0] = cv.take<void>(npix * 4 * HP * 2);
     ctx.dzb[1] = cv.take<void>(npix * 4 * HP * 2);
@@ -1064,6 +1112,11 @@ int plan_set_weights(clstm_plan* p, const float* const* params, cudaStream_t st)
   pack_head_weights_fwd_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, bh, static_cast<E*>(p->wh), p->bias_h,
                                                                p->cfg.out_channels, p->cfg.hidden, p->ctx.HP, p->NT);
   RC_TRY(after_launch("pack_head_weights_fwd_kernel"));
+  if (p->wz) {
+    pack_head_weights_rows_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, static_cast<E*>(p->wz), p->cfg.out_channels,
+                                                                p->cfg.hidden, p->ctx.HP);
+    RC_TRY(after_launch("pack_head_weights_rows_kernel"));
+  }
   if (p->cfg.training) {
     pack_head_weights_dgrad_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, static_cast<E*>(p->whd), p->cfg.out_channels,
                                                                    p->cfg.hidden, p->ctx.HP, p->KG);
@@ -1136,6 +1189,19 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
       hp.b_img = c.batch;
       hp.t0 = t;
       const long long images = contiguous ? static_cast<long long>(c.t_out) * c.batch : c.batch;
+      if (p->wz) {
+        HeadRowsParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.images = static_cast<int>(images);
+        rp.img_off = hp.seg[0].b_off;
+        rp.b_img = c.batch, rp.t0 = t, rp.t_out = c.t_out, rp.c_out = c.out_channels;
+        rp.chunks = HP / 64;
+        rp.bias = p->bias_h;
+        rp.y = y;
+        bool used = false;
+        RC_TRY((launch_head_rows<E>(ctx.dev, last.m_h128, p->m_wz, rp, geo, st, &used)));
+        if (used) continue;
+      }
       if (ctx.pair_ok && env_int("CLSTM_HALO2_HEAD", 0)) {
         bool used = false;
         RC_TRY((launch_halo2<E, EPI_HEAD>(ctx.dev, last.m_hhalo3, last.m_hhalo3, p->m_wh, p->m_wh, p->m_wh, p->m_wh, hp, geo,
@@ -1605,6 +1671,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   RC_TRY(make_map_act(&p->m_xcol128, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW, g.BH));
   RC_TRY(make_map_act(&p->m_xcol64, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW2, g.BH2));
   RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT / weight_boxes(p->NT)));
+  if (p->wz) RC_TRY(make_map_w(&p->m_wz, ctx.dtype, p->wz, 64, (ctx.HP / 64) * kHrN, kHrN));
   if (c.training) {
     RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));

@@ -322,6 +322,21 @@ __global__ void pack_head_weights_fwd_kernel(const float* __restrict__ w, const 
   }
 }
 
+// row-marching head (head_rows.cuh): Wz[chunk][n = tap*16 + co (144 rows)][k = c % 64] = Whead[co][c][0][tap]
+template <typename E>
+__global__ void pack_head_weights_rows_kernel(const float* __restrict__ w, E* __restrict__ wz, int c_out, int hid,
+                                              int HP) {
+  const size_t total = static_cast<size_t>(HP / 64) * 144 * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int kk = static_cast<int>(i % 64), n = static_cast<int>((i / 64) % 144), ch = static_cast<int>(i / (64 * 144));
+    const int tap = n / 16, co = n % 16, c = ch * 64 + kk;
+    float val = 0.f;
+    if (co < c_out && c < hid) val = w[(static_cast<size_t>(co) * hid + c) * 9 + tap];
+    wz[i] = Elem<E>::from_float(val);
+  }
+}
+
 // head dgrad: Whd[row = c (HP rows)][k = tap*c_out + co (padded to KG)] = Whead[co][c][0][tap]
 template <typename E>
 __global__ void pack_head_weights_dgrad_kernel(const float* __restrict__ w, E* __restrict__ wd, int c_out, int hid,
