@@ -428,9 +428,6 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? (env_int("CLSTM_STAGED", 1) ? 1 : 0) : 0;
   p.b_boxes = weight_boxes(p.n_tile);
   p.prod_serial = env_int("CLSTM_PROD_SERIAL", 0);
-  p.prod_groups = env_int(EPI == EPI_LSTM ? "CLSTM_PROD_GROUPS" : "CLSTM_PROD_GROUPS_SMALL", EPI == EPI_LSTM ? 1 : 1);
-  if (p.prod_groups < 1) p.prod_groups = 1;
-  if (p.prod_groups > 4) p.prod_groups = 4;
   p.dbg_no_tma = env_int("CLSTM_NOTMA", 0);
   p.hint_store = env_int("CLSTM_HINT_STORE", 0);
   p.hint_w = env_int("CLSTM_HINT_W", 0);
@@ -445,7 +442,6 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(CLSTM_EINVAL, "convgemm: not enough shared memory for n_tile=%d", p.n_tile);
   p.stages = stages;
-  if (p.prod_groups > stages) p.prod_groups = stages;
   const size_t smem = convgemm_smem_bytes(stages, p.n_tile, p.n_tiles, stg_half);
   static bool attr_set = false;
   if (!attr_set) {
@@ -791,7 +787,7 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.act_mode = env_int("CLSTM_ACT_MODE", 3);
   p.skip_mask = env_int("CLSTM_SKIP", 0);
   p.lsu_mask = env_int("CLSTM_LSU", 0);
-  if (ctx.pair_ok) {
+  if (ctx.pair_ok && !(g.in_col && env_int("CLSTM_PAIR", 0) == 2)) {  // CLSTM_PAIR=2: not for the xcol cell
     bool used = false;
     const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
     RC_TRY((launch_pairgemm<E, EPI_LSTM>(ctx.dev, halo ? *in.maphalo : *in.map128, halo ? cs.m_hhalo : cs.m_h128,

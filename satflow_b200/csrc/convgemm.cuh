@@ -61,7 +61,6 @@ struct ConvGemmParams {
   int stages;
   int hint_store, hint_w, hint_a;  // L2 cache hints: 0 none, 1 evict_first, 2 evict_last (stores / weights / A tiles)
   int dbg_no_tma;   // experiment: after the first ring fill reuse shared memory (no TMA loads) -> pure MMA rate
-  int prod_groups;  // lane groups of the TMA producer working on different stages concurrently (1..4)
   int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
   int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
   // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
@@ -296,16 +295,9 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // One lane per box: lane 0 loads the A tile, lanes 1..b_boxes one slice of the weight tile each.  A single
     // thread issuing every cp.async.bulk.tensor of a stage serialises on the issue latency (measured: the wgrad
     // kernel went from 555 to 1250 TFLOP/s when its 8 boxes per stage were spread over 8 lanes).
-    // prod_groups lane groups of (1 + b_boxes) lanes each take every prod_groups-th k-block, so several stages are
-    // being issued at once (one lane manages ~1 cp.async.bulk.tensor per 500-700 cycles).
-    const int lanes_per_group = p.prod_serial ? 1 : 1 + p.b_boxes;
-    const int pgroup = lane / lanes_per_group;
-    const int glane = lane % lanes_per_group;
-    if (pgroup < p.prod_groups) {
-      const int lane = glane;  // position inside the group: 0 = A box, 1.. = weight boxes
+    if (lane <= (p.prod_serial ? 0 : p.b_boxes)) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t kcount = 0;     // running k-block counter across tiles
       const int b_rows = p.n_tile / p.b_boxes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
@@ -319,14 +311,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const ConvSeg sg = p.seg[s];
           for (int dy = 0; dy < sg.kh; ++dy)
             for (int dx = 0; dx < sg.kw; ++dx)
-              for (int ch = 0; ch < sg.chunks; ++ch, ++kb, ++kcount) {
-                if (static_cast<int>(kcount % p.prod_groups) != pgroup) {  // another lane group owns this k-block
-                  if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                  }
-                  continue;
-                }
+              for (int ch = 0; ch < sg.chunks; ++ch, ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* a_dst = smem + stage * stage_bytes;
                 if (p.dbg_no_tma && (tile != static_cast<int>(blockIdx.x) || kb >= p.stages)) {
