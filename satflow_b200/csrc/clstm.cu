@@ -433,6 +433,14 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   p.hint_w = env_int("CLSTM_HINT_W", 0);
   p.hint_a = env_int("CLSTM_HINT_A", 0);
   if (EPI == EPI_STORE) p.skip_mask = env_int("CLSTM_SKIP", 0);
+  {
+    int kblocks = 0;
+    for (int s = 0; s < p.nseg; ++s) kblocks += p.seg[s].chunks * p.seg[s].kh * p.seg[s].kw;
+    p.rotate = (kblocks <= kKtabMax && kblocks > 1 && !p.dbg_no_tma && !p.prod_serial && p.b_boxes == 1 && !p.hint_a &&
+                !p.hint_w && env_int("CLSTM_ROTATE", 1))
+                   ? 1
+                   : 0;
+  }
   const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));

@@ -29,6 +29,7 @@ constexpr int kABytes = kTileM * 128;
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 384;
 constexpr int kTmemCols = 512;
+constexpr int kKtabMax = 64;       // k-block table entries (rotated K loop)
 // Epilogue staging, per half (4 warps = 128 pixel rows x one 16-channel group):
 //   [c_prev 8 KB][c 8 KB][h 4 KB][gates 4 x 4 KB]   (EPI_STORE uses the c slot only)
 constexpr int kStgCprev = 0, kStgC = 8192, kStgH = 16384, kStgG = 20480;
@@ -62,6 +63,7 @@ struct ConvGemmParams {
   int hint_store, hint_w, hint_a;  // L2 cache hints: 0 none, 1 evict_first, 2 evict_last (stores / weights / A tiles)
   int dbg_no_tma;   // experiment: after the first ring fill reuse shared memory (no TMA loads) -> pure MMA rate
   int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
+  int rotate;       // 1: tile t starts its K loop at k-block t % kblocks (needs kblocks <= kKtabMax), see producer
   int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
   // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
   const float* bias;  // [n_tiles * n_tile] in packed row order (all epilogues)
@@ -285,6 +287,15 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (p.bias != nullptr) {
     for (int i = threadIdx.x; i < p.n_tiles * p.n_tile; i += blockDim.x) bias_s[i] = p.bias[i];
   }
+  // k-block table for the rotated K loop: {segment, dx offset, dy offset, channel offset}
+  int4* ktab = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(bias_s + p.n_tiles * p.n_tile) + 15) & ~uintptr_t(15));
+  if (p.rotate && threadIdx.x < kblocks) {
+    int kb = threadIdx.x, sgi = 0;
+    while (kb >= p.seg[sgi].chunks * p.seg[sgi].kh * p.seg[sgi].kw) kb -= p.seg[sgi].chunks * p.seg[sgi].kh * p.seg[sgi].kw, ++sgi;
+    const ConvSeg sg = p.seg[sgi];
+    const int ch = kb % sg.chunks, tap = kb / sg.chunks;
+    ktab[threadIdx.x] = make_int4(sgi, tap % sg.kw - sg.kw / 2, tap / sg.kw - sg.kh / 2, ch * kBlockK);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -295,7 +306,41 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // One lane per box: lane 0 loads the A tile, lanes 1..b_boxes one slice of the weight tile each.  A single
     // thread issuing every cp.async.bulk.tensor of a stage serialises on the issue latency (measured: the wgrad
     // kernel went from 555 to 1250 TFLOP/s when its 8 boxes per stage were spread over 8 lanes).
-    if (lane <= (p.prod_serial ? 0 : p.b_boxes)) {
+    if (p.rotate) {
+      // Rotated K loop.  Every CTA walks the k-blocks of its tile in the same order, so at any moment all 148 SMs
+      // ask L2 for the SAME 32 KB weight k-block: those ~256 lines live in a few L2 slices, which serialise the
+      // requests while the other slices idle.  Starting tile t at k-block t % kblocks spreads the concurrent weight
+      // reads over the whole [n_tile x K] matrix.  (The accumulation order of a tile depends only on its index.)
+      if (lane < 2) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int boff0 = p.seg[0].b_off, boff1 = p.seg[1].b_off;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+          const int w0 = (mt % p.tiles_w) * p.BW;
+          const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
+          const int b = mt / (p.tiles_w * p.tiles_h);
+          int kb = tile % kblocks;
+          for (int i = 0; i < kblocks; ++i) {
+            const int4 e = ktab[kb];
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = smem + stage * stage_bytes;
+            if (lane == 0) {
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              tma_load_4d(a_dst, e.x ? &tmA1 : &tmA0, &full_bar[stage], e.w, w0 + e.y, h0 + e.z,
+                          b + (e.x ? boff1 : boff0));
+            } else {
+              tma_load_2d(a_dst + kABytes, &tmB, &full_bar[stage], kb * kBlockK, nt * p.n_tile);
+            }
+            if (++kb == kblocks) kb = 0;
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane <= (p.prod_serial ? 0 : p.b_boxes)) {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_tile / p.b_boxes;
@@ -649,7 +694,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
 inline size_t convgemm_smem_bytes(int stages, int n_tile, int n_tiles, int stg_half = 0) {
   return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 2 * static_cast<size_t>(stg_half) +
-         (2 * kMaxStages + 8) * 8 + 16 + static_cast<size_t>(n_tiles) * n_tile * 4 + 64;
+         (2 * kMaxStages + 8) * 8 + 16 + static_cast<size_t>(n_tiles) * n_tile * 4 + 64 + kKtabMax * 16 + 16;
 }
 
 }  // namespace clstm
