@@ -591,6 +591,7 @@ int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtenso
   p.split_col = split_col;
   p.lbw = 0;
   while ((1 << p.lbw) < g.BW) ++p.lbw;
+  p.rotate = env_int("CLSTM_ROTATE_D", 0) ? 1 : 0;  // measured: no gain for dgrad (weights are 1/3 of its operand bytes)
   int stages = (dev.smem_optin - static_cast<int>(dgradT_smem_bytes(0))) / kDtStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return 0;
@@ -620,6 +621,7 @@ int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const C
   p.m_tiles = 1;
   p.lbw = 0;
   while ((1 << p.lbw) < g.BW) ++p.lbw;
+  p.rotate = env_int("CLSTM_ROTATE_D", 0) ? 1 : 0;  // measured: no gain for dgrad (weights are 1/3 of its operand bytes)
   int stages = (dev.smem_optin - static_cast<int>(dgradTf_smem_bytes(0))) / kDtStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(CLSTM_EINVAL, "dgradT_fused: not enough shared memory");

@@ -30,6 +30,7 @@ struct DgradTParams {
   int stages;
   int split_col;   // output channels [0, split) -> X0 (dx), [split, ...) -> X1 (dh_prev); multiple of 64
   int lbw;         // log2(BW)
+  int rotate;      // 1: unit u starts its K loop at k-block u % kblocks (spreads the concurrent weight reads over L2)
 };
 
 inline size_t dgradT_smem_bytes(int stages) {
@@ -93,24 +94,33 @@ dgradT_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ 
         const int mtile = unit % p.m_tiles;
         int w0 = 0, h0 = 0, b = 0;
         if (lane > 0) tile_origin(unit, lane - 1, w0, h0, b);
-        int kb = 0;
-        for (int dy = 0; dy < p.seg.kh; ++dy)
-          for (int dx = 0; dx < p.seg.kw; ++dx)
-            for (int ch = 0; ch < p.seg.chunks; ++ch, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* dst = smem + stage * kDtStageBytes;
-              if (lane == 0) {
-                mbar_expect_tx(&full_bar[stage], kDtStageBytes);
-                tma_load_2d(dst, &tmW, &full_bar[stage], kb * kBlockK, mtile * 128);
-              } else {
-                tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmDz, &full_bar[stage], ch * kBlockK,
-                            w0 + dx - p.seg.kw / 2, h0 + dy - p.seg.kh / 2, b + p.seg.b_off);
-              }
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
+        // rotated start: (dy, dx, ch) decoded once per unit, then stepped with wrap-around
+        const int kblocks = taps * p.seg.chunks;
+        int kb = p.rotate ? unit % kblocks : 0;
+        int ch = kb % p.seg.chunks, dx = (kb / p.seg.chunks) % p.seg.kw, dy = kb / (p.seg.chunks * p.seg.kw);
+        for (int i = 0; i < kblocks; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * kDtStageBytes;
+          if (lane == 0) {
+            mbar_expect_tx(&full_bar[stage], kDtStageBytes);
+            tma_load_2d(dst, &tmW, &full_bar[stage], kb * kBlockK, mtile * 128);
+          } else {
+            tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmDz, &full_bar[stage], ch * kBlockK,
+                        w0 + dx - p.seg.kw / 2, h0 + dy - p.seg.kh / 2, b + p.seg.b_off);
+          }
+          ++kb;
+          if (++ch == p.seg.chunks) {
+            ch = 0;
+            if (++dx == p.seg.kw) {
+              dx = 0;
+              if (++dy == p.seg.kh) dy = 0, kb = 0;
             }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -300,24 +310,32 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         int w0 = 0, h0 = 0, b = 0;
         if (lane > 0) tile_origin(unit, lane - 1, w0, h0, b);
-        int kb = 0;
-        for (int dy = 0; dy < p.seg.kh; ++dy)
-          for (int dx = 0; dx < p.seg.kw; ++dx)
-            for (int ch = 0; ch < p.seg.chunks; ++ch, ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* dst = smem + stage * kDtStageBytes;
-              if (lane == 0) {
-                mbar_expect_tx(&full_bar[stage], kDtStageBytes);
-                tma_load_2d(dst, &tmW, &full_bar[stage], kb * kBlockK, 0);
-              } else {
-                tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmDz, &full_bar[stage], ch * kBlockK,
-                            w0 + dx - p.seg.kw / 2, h0 + dy - p.seg.kh / 2, b + p.seg.b_off);
-              }
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
+        const int kblocks = taps * p.seg.chunks;
+        int kb = p.rotate ? unit % kblocks : 0;  // rotated start, see dgradT_kernel
+        int ch = kb % p.seg.chunks, dx = (kb / p.seg.chunks) % p.seg.kw, dy = kb / (p.seg.chunks * p.seg.kw);
+        for (int i = 0; i < kblocks; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * kDtStageBytes;
+          if (lane == 0) {
+            mbar_expect_tx(&full_bar[stage], kDtStageBytes);
+            tma_load_2d(dst, &tmW, &full_bar[stage], kb * kBlockK, 0);
+          } else {
+            tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmDz, &full_bar[stage], ch * kBlockK,
+                        w0 + dx - p.seg.kw / 2, h0 + dy - p.seg.kh / 2, b + p.seg.b_off);
+          }
+          ++kb;
+          if (++ch == p.seg.chunks) {
+            ch = 0;
+            if (++dx == p.seg.kw) {
+              dx = 0;
+              if (++dy == p.seg.kh) dy = 0, kb = 0;
             }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
