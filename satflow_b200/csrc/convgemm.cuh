@@ -310,7 +310,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       // Rotated K loop.  Every CTA walks the k-blocks of its tile in the same order, so at any moment all 148 SMs
       // ask L2 for the SAME 32 KB weight k-block: those ~256 lines live in a few L2 slices, which serialise the
       // requests while the other slices idle.  Starting tile t at k-block t % kblocks spreads the concurrent weight
-      // reads over the whole [n_tile x K] matrix.  (The accumulation order of a tile depends only on its index.)
+      // reads over the whole [n_tile x K] matrix.  (The accumulation order of a tile depends only on its position inside
+      // the image, so a sample's result does not depend on where it sits in the batch.)
       if (lane < 2) {
         int stage = 0;
         uint32_t phase = 0;
@@ -320,7 +321,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const int w0 = (mt % p.tiles_w) * p.BW;
           const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
           const int b = mt / (p.tiles_w * p.tiles_h);
-          int kb = tile % kblocks;
+          int kb = (mt % (p.tiles_w * p.tiles_h) + nt) % kblocks;  // position inside the image: batch-index independent
           for (int i = 0; i < kblocks; ++i) {
             const int4 e = ktab[kb];
             mbar_wait(&empty_bar[stage], phase ^ 1);
