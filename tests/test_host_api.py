@@ -139,3 +139,24 @@ def test_yaml_and_lightning_checkpoint_helpers(tmp_path):
     hp = m2.load_lightning_checkpoint(str(ck))
     assert hp["hidden_dim"] == 16
     assert torch.equal(m2.state_dict()["model.decoder_CNN.bias"], sd["model.decoder_CNN.bias"])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) prints ONE JSON line with the same
+    metric / unit / config as the CUDA arm plus the reference-arm keys; it must work without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
