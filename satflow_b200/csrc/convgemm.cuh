@@ -399,6 +399,10 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // The descriptors of the NEXT stage are built right after the MMAs of the current one are issued: with a
+      // 3-stage ring nothing between "data landed" and "first MMA issued" is hidden (DESIGN.md finding 8).
+      uint64_t adesc = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + kABytes, 16, 1024);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -406,9 +410,6 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per K=16 step inside the 128-B swizzle row (start-address field is in 16-B units)
@@ -419,6 +420,9 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             stage = 0;
             phase ^= 1;
           }
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+          bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         acc ^= 1;

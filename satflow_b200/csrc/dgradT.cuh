@@ -130,6 +130,8 @@ dgradT_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ 
       const int kblocks = taps * p.seg.chunks;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      uint64_t adesc = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + 16384, 16, 1024);
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -137,9 +139,6 @@ dgradT_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t base = smem_u32(smem + stage * kDtStageBytes);
-          const uint64_t adesc = make_smem_desc_sw128(base, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(base + 16384, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
@@ -147,6 +146,9 @@ dgradT_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ 
             stage = 0;
             phase ^= 1;
           }
+          const uint32_t base = smem_u32(smem + stage * kDtStageBytes);  // next stage's descriptors, off the wait path
+          adesc = make_smem_desc_sw128(base, 16, 1024);
+          bdesc = make_smem_desc_sw128(base + 16384, 16, 1024);
         }
         umma_commit(&tmem_full[acc]);
         acc ^= 1;
@@ -344,6 +346,8 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
       const int kblocks = taps * p.seg.chunks;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      uint64_t adesc = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + 16384, 16, 1024);
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -351,9 +355,6 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t base = smem_u32(smem + stage * kDtStageBytes);
-          const uint64_t adesc = make_smem_desc_sw128(base, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(base + 16384, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
@@ -361,6 +362,9 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
             stage = 0;
             phase ^= 1;
           }
+          const uint32_t base = smem_u32(smem + stage * kDtStageBytes);  // next stage's descriptors, off the wait path
+          adesc = make_smem_desc_sw128(base, 16, 1024);
+          bdesc = make_smem_desc_sw128(base + 16384, 16, 1024);
         }
         umma_commit(&tmem_full[acc]);
         acc ^= 1;
