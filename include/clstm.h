@@ -152,6 +152,15 @@ int clstm_mse_loss_grad(const float* y, const float* target, int batch, int chan
 /* Number of kernels this library has launched since load (all plans, this process). */
 uint64_t clstm_launch_count(void);
 
+/* In-situ launch trace (measurement only).  clstm_trace_enable(capacity > 0) makes every subsequent launch of this
+ * library record a CUDA event on the stream of the enclosing API call (capacity = maximum number of events kept;
+ * 0 disables and frees them).  clstm_trace_report synchronises on the last event, writes a per-kernel table
+ * (count, total ms, share, average us; intervals = time between consecutive launch completions on that stream) into
+ * buf, resets the trace and returns the number of bytes written (negative: error code).  Unlike the isolated
+ * timings of clstm_plan_profile_kernel these are taken under the clocks of the real step. */
+int clstm_trace_enable(int capacity);
+long long clstm_trace_report(char* buf, size_t cap);
+
 /* ---- bring-up self tests (device micro-experiments; see tests/test_gpu_selftest.py) -------- */
 /* Shifted shared-memory descriptor experiment: out_max_abs_err is DEVICE memory for
  * n_variants (<= 2) x n_shifts (<= 16) floats, max |D - expected| per (variant, row shift). */

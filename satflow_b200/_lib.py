@@ -66,6 +66,8 @@ _PROTOTYPES = {
     "clstm_cell_backward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_void_p]),
     "clstm_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_launch_count": (c_uint64, []),
+    "clstm_trace_enable": (c_int, [c_int]),
+    "clstm_trace_report": (ctypes.c_longlong, [ctypes.c_char_p, c_size_t]),
     "clstm_selftest_shifted_desc": (c_int, [c_void_p, c_int, c_int, c_void_p]),
 }
 
@@ -110,3 +112,17 @@ def ptr_array(tensors):
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
     return arr
+
+
+def trace_enable(capacity: int = 4096) -> None:
+    """Record one CUDA event after every library launch (0 disables); see clstm_trace_enable in include/clstm.h."""
+    check(lib().clstm_trace_enable(int(capacity)))
+
+
+def trace_report() -> str:
+    """Per-kernel in-situ timing table of the launches since trace_enable / the last report."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().clstm_trace_report(buf, len(buf))
+    if n < 0:
+        check(int(n))
+    return buf.value.decode("utf-8", "replace")

@@ -55,10 +55,34 @@ int fail(int code, const char* fmt, ...) {
     if (rc__ != 0) return rc__; \
   } while (0)
 
+// In-situ launch trace (clstm_trace_enable / clstm_trace_report): one CUDA event after every launch on the stream of
+// the current API call, so per-kernel durations can be read under the power state of the real step — isolated
+// kernel timings and the step disagree on a power-capped B200 (DESIGN.md finding 9).  Off by default.
+struct LaunchTrace {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> name;  // nullptr = start of an API call (the interval before it is time outside the library)
+  size_t n = 0;
+  void mark(const char* what) {
+    if (!on || n >= ev.size()) return;
+    if (cudaEventRecord(ev[n], st) != cudaSuccess) return;
+    name[n++] = what;
+  }
+};
+LaunchTrace g_trace;
+
+inline void trace_begin(void* stream) {
+  if (!g_trace.on) return;
+  g_trace.st = static_cast<cudaStream_t>(stream);
+  g_trace.mark(nullptr);
+}
+
 inline int after_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(CLSTM_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  if (g_trace.on) g_trace.mark(what);
   return 0;
 }
 
@@ -1564,6 +1588,69 @@ const char* clstm_last_error(void) { return g_err; }
 int clstm_abi_version(void) { return CLSTM_ABI_VERSION; }
 uint64_t clstm_launch_count(void) { return g_launches.load(); }
 
+int clstm_trace_enable(int capacity) {
+  for (cudaEvent_t e : g_trace.ev) cudaEventDestroy(e);
+  g_trace.ev.clear();
+  g_trace.name.clear();
+  g_trace.n = 0;
+  g_trace.on = false;
+  if (capacity <= 0) return 0;
+  g_trace.ev.resize(static_cast<size_t>(capacity));
+  g_trace.name.assign(static_cast<size_t>(capacity), nullptr);
+  for (auto& e : g_trace.ev) CU_TRY(cudaEventCreate(&e));
+  g_trace.on = true;
+  return 0;
+}
+
+long long clstm_trace_report(char* buf, size_t cap) {
+  if (!buf || cap == 0) return fail(CLSTM_EINVAL, "null argument");
+  buf[0] = 0;
+  const size_t n = g_trace.n;
+  if (n < 2) return 0;
+  CU_TRY(cudaEventSynchronize(g_trace.ev[n - 1]));
+  struct Row {
+    const char* name;
+    long long count;
+    double ms;
+  };
+  std::vector<Row> rows;
+  double total = 0.0;
+  for (size_t i = 1; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_trace.ev[i - 1], g_trace.ev[i]) != cudaSuccess) continue;
+    const char* nm = g_trace.name[i] ? g_trace.name[i] : "(outside the library: between API calls)";
+    Row* r = nullptr;
+    for (auto& x : rows)
+      if (strcmp(x.name, nm) == 0) r = &x;
+    if (!r) {
+      rows.push_back(Row{nm, 0, 0.0});
+      r = &rows.back();
+    }
+    r->count += 1;
+    r->ms += ms;
+    total += ms;
+  }
+  for (size_t i = 0; i < rows.size(); ++i)  // sort by total time, descending
+    for (size_t j = i + 1; j < rows.size(); ++j)
+      if (rows[j].ms > rows[i].ms) std::swap(rows[i], rows[j]);
+  size_t off = 0;
+  auto put = [&](const char* fmt, ...) {
+    if (off >= cap - 1) return;
+    va_list ap;
+    va_start(ap, fmt);
+    const int w = vsnprintf(buf + off, cap - off, fmt, ap);
+    va_end(ap);
+    if (w > 0) off += static_cast<size_t>(w) < cap - off ? static_cast<size_t>(w) : cap - off - 1;
+  };
+  put("%zu events, %.3f ms between the first and the last%s\n", n, total,
+      n >= g_trace.ev.size() ? " (capacity reached: later launches were dropped)" : "");
+  for (const Row& r : rows)
+    put("%10.3f ms %5.1f%%  n=%5lld  avg=%9.1f us  %s\n", r.ms, 100.0 * r.ms / (total > 0 ? total : 1), r.count,
+        1e3 * r.ms / r.count, r.name);
+  g_trace.n = 0;
+  return static_cast<long long>(off);
+}
+
 int clstm_device_check(int ordinal) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -1734,6 +1821,7 @@ int clstm_rollout_forward(clstm_plan_t* p, const float* x, float* y, void* strea
 }
 
 int clstm_rollout_forward_layout(clstm_plan_t* p, const float* x, int x_layout, float* y, void* stream) {
+  trace_begin(stream);
   if (!p || !x || !y) return fail(CLSTM_EINVAL, "null argument");
   if (!p->bound || !p->weights_set) return fail(CLSTM_ESTATE, "forward before bind / set_weights");
   if (x_layout != CLSTM_X_BTCHW && x_layout != CLSTM_X_BTHWC) return fail(CLSTM_EINVAL, "unknown x layout %d", x_layout);
@@ -1745,6 +1833,7 @@ int clstm_rollout_forward_layout(clstm_plan_t* p, const float* x, int x_layout, 
 
 int clstm_rollout_backward(clstm_plan_t* p, const float* dy, const float* y, float* const* grads, int n_grads,
                            int accumulate, void* stream) {
+  trace_begin(stream);
   if (!p || !dy || !y || !grads) return fail(CLSTM_EINVAL, "null argument");
   if (!p->cfg.training) return fail(CLSTM_ESTATE, "backward on a plan created with training = 0");
   if (!p->forward_done) return fail(CLSTM_ESTATE, "backward before forward");
@@ -1924,6 +2013,7 @@ int clstm_cell_backward(clstm_cell_plan_t* p, const float* dh_next, const float*
 // ---------------------------------------------------------------------------- fused loss
 int clstm_mse_loss_grad(const float* y, const float* target, int batch, int channels, int t_out, int height, int width,
                         float* dy, float* partial, float* out, void* stream) {
+  trace_begin(stream);
   if (!y || !target || !partial || !out) return fail(CLSTM_EINVAL, "null argument");
   if (batch < 1 || channels < 1 || t_out < 1 || t_out > 1024 || height < 1 || width < 1)
     return fail(CLSTM_EINVAL, "bad shape (t_out must be <= 1024)");
