@@ -247,7 +247,6 @@ int pad_hidden(int hid) {
 
 const int kPackBlocks = 148 * 8;
 const int kGateGradBlocks = 148 * 4;
-const int kHeadBiasChunks = 148;
 
 // Everything a cell step needs besides the cell itself.
 struct Ctx {
@@ -1062,7 +1061,8 @@ struct clstm_plan {
   float* bias_h = nullptr;    // fp32 [NT]
   void* whd = nullptr;        // E [n_tile_hd rows = HP][KG]
   float* hpart = nullptr;     // fp32 [splits][128*(KG/128)][HP]
-  float* hbpart = nullptr;    // fp32 [C_out][kHeadBiasChunks]
+  float* hbpart = nullptr;    // fp32 [C_out][batch * hb_chunks]
+  int hb_chunks = 1;          // pieces per (b, c) run in head_grad_stats_kernel
   int head_splits = 0, head_group = 0, n_tile_hd = 0;
   CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16, m_wz;
 };
@@ -1091,7 +1091,14 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
     p->dstack = cv.take<float>(npix * HP * 4);
     p->whd = cv.take<void>(static_cast<size_t>(HP) * p->KG * 2);
     p->hpart = cv.take<float>(static_cast<size_t>(p->head_splits) * p->KG * HP * 4);
-    p->hbpart = cv.take<float>(static_cast<size_t>(c.out_channels) * kHeadBiasChunks * 4);
+    {  // about 8 blocks per SM, at least 4096 elements per block
+      const size_t per_b = static_cast<size_t>(c.t_out) * c.height * c.width;
+      int chunks = (8 * 148 + c.batch * c.out_channels - 1) / (c.batch * c.out_channels);
+      const size_t max_chunks = per_b / 4096 > 0 ? per_b / 4096 : 1;
+      if (static_cast<size_t>(chunks) > max_chunks) chunks = static_cast<int>(max_chunks);
+      p->hb_chunks = chunks < 1 ? 1 : chunks;
+    }
+    p->hbpart = cv.take<float>(static_cast<size_t>(c.out_channels) * c.batch * p->hb_chunks * 4);
   }
   p->ws_bytes = align_up(cv.off, 1024);
 }
@@ -1254,13 +1261,15 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   const size_t npix = geo.npix();
   const int HP = ctx.HP;
   const int L = p->L, ncell = p->ncell;
-  const size_t ny = static_cast<size_t>(c.batch) * c.out_channels * c.t_out * c.height * c.width;
-
-  // loss scale for the 16-bit gradient operands (device side, no sync)
+  // loss scale for the 16-bit gradient operands (device side, no sync) and the head bias gradient (sum of dlogit,
+  // unscaled): one pass over dy and y
   CU_TRY(cudaMemsetAsync(ctx.amax, 0, 4, st));
-  if (!(c.grad_scale > 0.f)) {
-    head_grad_amax_kernel<<<kPackBlocks, 256, 0, st>>>(dy, y, ny, ctx.amax);
-    RC_TRY(after_launch("head_grad_amax_kernel"));
+  {
+    const size_t per_b = static_cast<size_t>(c.t_out) * c.height * c.width;
+    dim3 grid(p->hb_chunks, c.batch * c.out_channels);
+    head_grad_stats_kernel<<<grid, 256, 0, st>>>(dy, y, p->hbpart, (c.grad_scale > 0.f) ? nullptr : ctx.amax, c.batch,
+                                                 c.out_channels, per_b, p->hb_chunks);
+    RC_TRY(after_launch("head_grad_stats_kernel"));
   }
   choose_scale_kernel<<<1, 1, 0, st>>>(ctx.amax, ctx.scale, ctx.dtype == CLSTM_F16 ? 1024.f : 1.f, c.grad_scale);
   RC_TRY(after_launch("choose_scale_kernel"));
@@ -1269,18 +1278,11 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     p->cells[k].bwd_started = false;
     CU_TRY(cudaMemsetAsync(p->cells[k].dc, 0, npix * HP * 4, st));
   }
-  // head bias gradient: sum of dlogit (unscaled, straight from dy and y)
-  {
-    dim3 grid(kHeadBiasChunks, c.out_channels);
-    head_bias_partial_kernel<<<grid, 256, 0, st>>>(dy, y, p->hbpart, c.batch, c.out_channels, c.t_out, c.height,
-                                                   c.width);
-    RC_TRY(after_launch("head_bias_partial_kernel"));
-    float* db = grads[2 * ncell + 1];
-    if (db) {
-      reduce_rows_kernel<<<(c.out_channels + 63) / 64, 64, 0, st>>>(p->hbpart, db, c.out_channels, kHeadBiasChunks, 1,
-                                                                    kHeadBiasChunks, 1.f, accumulate);
-      RC_TRY(after_launch("reduce_rows_kernel"));
-    }
+  if (float* db = grads[2 * ncell + 1]) {
+    const int rows = c.batch * p->hb_chunks;
+    reduce_rows_kernel<<<(c.out_channels + 63) / 64, 64, 0, st>>>(p->hbpart, db, c.out_channels, rows, 1, rows, 1.f,
+                                                                  accumulate);
+    RC_TRY(after_launch("reduce_rows_kernel"));
   }
 
   // Backward schedule.  Per cell step: G = gate-grad (HBM bound) -> D = dgrad (tensor bound, on the critical

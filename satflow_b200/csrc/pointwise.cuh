@@ -512,29 +512,56 @@ __global__ void head_grad_col_kernel(const float* __restrict__ dyv, const float*
   }
 }
 
-// head bias gradient: db[co] = sum dy*y*(1-y).  grid = (chunks, C); partial[co][chunk], fixed order.
+// One pass over dy and y (B, C, T, H, W) for both statistics the head backward needs before anything else:
+//   partial[co][b * chunks + chunk] = sum over the chunk of dlogit = dy * y * (1 - y)     (head bias gradient)
+//   *amax_bits = max |dlogit|                                                            (loss scale; optional)
+// Block (chunk, b*C + co) walks a contiguous piece of one (b, co) run of T*H*W floats: no per-element index
+// arithmetic, float4 loads when the run length allows.
 __global__ void __launch_bounds__(256)
-head_bias_partial_kernel(const float* __restrict__ dyv, const float* __restrict__ y, float* __restrict__ partial,
-                         int B, int C, int T, int H, int W) {
-  const int co = blockIdx.y;
-  const size_t per_b = static_cast<size_t>(T) * H * W;
-  const size_t total = static_cast<size_t>(B) * per_b;
-  float s = 0.f;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t b = i / per_b, r = i % per_b;
-    const size_t idx = (b * C + co) * per_b + r;
-    const float yy = __ldg(y + idx);
-    s += __ldg(dyv + idx) * yy * (1.f - yy);
+head_grad_stats_kernel(const float* __restrict__ dyv, const float* __restrict__ y, float* __restrict__ partial,
+                       unsigned int* __restrict__ amax_bits, int B, int C, size_t per_b, int chunks) {
+  const int bc = blockIdx.y, chunk = blockIdx.x;
+  const int b = bc / C, co = bc % C;
+  const size_t base = static_cast<size_t>(bc) * per_b;
+  float s = 0.f, m = 0.f;
+  if ((per_b & 3) == 0) {
+    const size_t n4 = per_b >> 2;
+    const size_t lo = n4 * chunk / chunks, hi = n4 * (chunk + 1) / chunks;
+    const float4* d4 = reinterpret_cast<const float4*>(dyv + base);
+    const float4* y4 = reinterpret_cast<const float4*>(y + base);
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float4 a = __ldg(d4 + i), yy = __ldg(y4 + i);
+      const float v0 = a.x * yy.x * (1.f - yy.x), v1 = a.y * yy.y * (1.f - yy.y);
+      const float v2 = a.z * yy.z * (1.f - yy.z), v3 = a.w * yy.w * (1.f - yy.w);
+      s += (v0 + v1) + (v2 + v3);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
+    }
+  } else {
+    const size_t lo = per_b * chunk / chunks, hi = per_b * (chunk + 1) / chunks;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float yy = __ldg(y + base + i);
+      const float v = __ldg(dyv + base + i) * yy * (1.f - yy);
+      s += v;
+      m = fmaxf(m, fabsf(v));
+    }
   }
-  __shared__ float red[256];
-  red[threadIdx.x] = s;
+  __shared__ float red_s[256];
+  __shared__ float red_m[256];
+  red_s[threadIdx.x] = s;
+  red_m[threadIdx.x] = m;
   __syncthreads();
   for (int st = 128; st > 0; st >>= 1) {
-    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    if (threadIdx.x < st) {
+      red_s[threadIdx.x] += red_s[threadIdx.x + st];
+      red_m[threadIdx.x] = fmaxf(red_m[threadIdx.x], red_m[threadIdx.x + st]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[static_cast<size_t>(co) * gridDim.x + blockIdx.x] = red[0];
+  if (threadIdx.x == 0) {
+    partial[static_cast<size_t>(co) * (static_cast<size_t>(B) * chunks) + static_cast<size_t>(b) * chunks + chunk] = red_s[0];
+    const float mm = red_m[0];
+    if (amax_bits != nullptr && mm > 0.f && mm < 3.0e38f) atomicMax(amax_bits, __float_as_uint(mm));
+  }
 }
 
 // out[i] = scale * sum_r partial[r*stride_r + idx(i)]   generic strided split reduction
@@ -604,30 +631,6 @@ __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, fl
   for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
   s *= scale;
   dw[i] = accumulate ? dw[i] + s : s;
-}
-
-// ------------------------------------------------------------------------------------------
-// Loss-scale selection for 16-bit gradient operands.  amax_bits <- max |dy*y*(1-y)| (as float bits;
-// non-negative floats order like unsigned ints), then scale[0] = S = 2^floor(log2(target/amax)),
-// scale[1] = 1/S.  Everything stays on the device: no host synchronisation.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-head_grad_amax_kernel(const float* __restrict__ dyv, const float* __restrict__ y, size_t n,
-                      unsigned int* __restrict__ amax_bits) {
-  float m = 0.f;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float yy = __ldg(y + i);
-    m = fmaxf(m, fabsf(__ldg(dyv + i) * yy * (1.f - yy)));
-  }
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float red[8];
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int wv = 1; wv < 8; ++wv) m = fmaxf(m, red[wv]);
-    if (m > 0.f && m < 3.0e38f) atomicMax(amax_bits, __float_as_uint(m));
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -714,6 +717,10 @@ abs_amax_kernel(const float* __restrict__ a, size_t n, unsigned int* __restrict_
   }
 }
 
+// Loss-scale selection for 16-bit gradient operands.  amax_bits = max |dy*y*(1-y)| as float bits (non-negative floats
+// order like unsigned ints; written by head_grad_stats_kernel), then scale[0] = S = 2^floor(log2(target/amax)) and
+// scale[1] = 1/S; a positive `fixed` overrides it (clstm_config_t.grad_scale).  S is a power of two, so scaling and
+// un-scaling are exact.
 __global__ void choose_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale,
                                     float target, float fixed) {
   float s = fixed;
