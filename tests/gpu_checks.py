@@ -27,6 +27,9 @@ def cell_case(B, cin, hid, H, W, kh, kw, dtype="fp16", seed=0, backward=True) ->
     from satflow_b200 import ConvLSTMCell
 
     g = torch.Generator().manual_seed(seed)
+    # the cell's weights come from torch's default init, i.e. from the GLOBAL generator: seed it, otherwise the case
+    # depends on whatever ran before it (a 3-pixel case then misses the tolerance once in ~40 runs by rounding luck)
+    torch.manual_seed(1000 + seed)
     cell = ConvLSTMCell(cin, hid, (kh, kw), True)
     cell.operand_dtype = dtype
     x = torch.randn(B, cin, H, W, generator=g)
