@@ -247,6 +247,7 @@ int pad_hidden(int hid) {
 
 const int kPackBlocks = 148 * 8;
 const int kGateGradBlocks = 148 * 4;
+const int kBiasRowsMax = 148 * 16;  // bias partial rows: one per gate-worker warp of a wgrad CTA (>= kGateGradBlocks)
 
 // Everything a cell step needs besides the cell itself.
 struct Ctx {
@@ -378,7 +379,7 @@ void carve_cell(Carver& cv, CellState& cs, const Ctx& ctx) {
     cs.dxb = cs.with_x ? cv.take<float>(npix * cs.g.CIP * 4) : nullptr;
     cs.dc = cv.take<float>(npix * HP * 4);
     cs.wpart = cv.take<float>(static_cast<size_t>(cs.wg_splits) * 4 * HP * cs.Kf * 4);
-    cs.bpart = cv.take<float>(static_cast<size_t>(kGateGradBlocks) * 4 * HP * 4);
+    cs.bpart = cv.take<float>(static_cast<size_t>(kBiasRowsMax) * 4 * HP * 4);
   }
 }
 
@@ -742,7 +743,7 @@ int launch_dgradT_halo(const DeviceInfo& dev, const CUtensorMap& row256, const C
 
 template <typename E>
 int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
-                 WgradParams p, const Geo& g, long long images, cudaStream_t st) {
+                 WgradParams p, const Geo& g, long long images, cudaStream_t st, const WgGateWork* gate = nullptr) {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW2, p.BH = g.BH2, p.tiles_w = g.tiles_w2, p.tiles_h = g.tiles_h2;
   p.num_p_tiles = static_cast<int>(images) * g.tiles_w2 * g.tiles_h2;
@@ -755,12 +756,20 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   const size_t smem = wgrad_smem_bytes(0, 0) + static_cast<size_t>(stages) * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
     attr_set = true;
   }
   const int groups = (p.total_blocks + p.group_size - 1) / p.group_size;
   const int grid = groups * p.n_blocks * p.splits;
-  wgrad_kernel<E><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p);
+  if (gate != nullptr) {
+    if (grid > kBiasRowsMax / 16) return fail(CLSTM_EINVAL, "wgrad + gate workers: grid %d too large", grid);
+    wgrad_kernel<E, true><<<grid, kWgThreads + kWgGateThreads, smem, st>>>(a, b0, b1, p, *gate);
+    return after_launch("wgrad_gate_kernel");
+  }
+  WgGateWork none;
+  memset(&none, 0, sizeof(none));
+  wgrad_kernel<E, false><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p, none);
   return after_launch("wgrad_kernel");
 }
 
@@ -970,7 +979,8 @@ inline bool fuse_supported(const Ctx& ctx) {
 }
 
 template <typename E>
-int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st, int buf = 0) {
+int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int first, cudaStream_t st, int buf = 0,
+               const WgGateWork* gate = nullptr) {
   // dW += im2col([x, h_prev])^T dz, accumulated over the cell's time steps
   const CellGeom& g = cs.g;
   const Geo& geo = ctx.geo;
@@ -992,9 +1002,9 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
   if (!g.in_col && g.kh == 3 && g.kw == 3 && g.CIP == 64 && ctx.HP == 64 && geo.BW2 == 64 && geo.BH2 == 1 &&
       cs.wg_group == 6 && cs.wg_total == 18 && in.map66 != nullptr && env_int("CLSTM_WG_HALO", 1)) {
     p.halo = 1;
-    return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st);
+    return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st, gate);
   }
-  return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st);
+  return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st, gate);
 }
 
 template <typename E>
@@ -1010,7 +1020,8 @@ int cell_backward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp
 }
 
 // Reduce the split partial sums into reference-layout gradients (unscaled by 1/S).
-int cell_finalize(const Ctx& ctx, CellState& cs, float* dw, float* db, int accumulate, cudaStream_t st) {
+int cell_finalize(const Ctx& ctx, CellState& cs, float* dw, float* db, int accumulate, cudaStream_t st,
+                  int bias_rows = kGateGradBlocks) {
   const CellGeom& g = cs.g;
   if (dw) {
     cell_wgrad_finalize_kernel<<<kPackBlocks, 256, 0, st>>>(cs.wpart, dw, g, cs.wg_splits, ctx.scale + 1,
@@ -1018,7 +1029,7 @@ int cell_finalize(const Ctx& ctx, CellState& cs, float* dw, float* db, int accum
     RC_TRY(after_launch("cell_wgrad_finalize_kernel"));
   }
   if (db) {
-    cell_bias_finalize_kernel<<<(4 * g.hid + 255) / 256, 256, 0, st>>>(cs.bpart, db, kGateGradBlocks, g.hid,
+    cell_bias_finalize_kernel<<<(4 * g.hid + 255) / 256, 256, 0, st>>>(cs.bpart, db, bias_rows, g.hid,
                                                                        ctx.HP, ctx.scale + 1, accumulate);
     RC_TRY(after_launch("cell_bias_finalize_kernel"));
   }
@@ -1379,7 +1390,55 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   // allow, so the HBM-bound pointwise pass overlaps the tensor-bound GEMM.  dz alternates between two buffers
   // (dgrad n reads dz[b] through TMA while its epilogue writes dz[b^1]).
   const bool fuse = !overlap && L >= 2 && fuse_supported(ctx);
-  if (fuse) {
+  // Experimental alternative (CLSTM_WG_GATE=1, off): the gate gradient of step n+1 rides along with WGRAD n instead
+  // of the dgrad epilogue — 16 extra warps in the wgrad CTAs (wgrad.cuh), plain dgradT writes dx again.
+  const bool wg_gate = !overlap && HP == 64 && npix * 4 * HP < (1ull << 32) && env_int("CLSTM_WG_GATE", 0);
+  int bias_rows = kGateGradBlocks;
+  if (wg_gate) {
+    bias_rows = kBiasRowsMax;
+    for (int k = 0; k < ncell; ++k)
+      CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0, static_cast<size_t>(kBiasRowsMax) * 4 * HP * 4, st));
+    int b = 0;
+    bool gate_done = false;
+    for (size_t n = 0; n < ops.size(); ++n) {
+      const BackOp& o = ops[n];
+      CellState& cs = p->cells[o.k];
+      const InputRef in = plan_input(p, o.k, o.t);
+      const int first = cs.bwd_started ? 0 : 1;
+      cs.bwd_started = true;
+      if (!gate_done) {
+        if (o.head) RC_TRY(head_back(o.t));
+        const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(o.t) * npix * 4 * HP;
+        const float* c_prev = (o.t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, o.t)) * npix * HP;
+        const float* c_next = cs.c + static_cast<size_t>(cslot(cs, o.t + 1)) * npix * HP;
+        const float* own = (o.t == cs.T - 1) ? nullptr : cs.dh_own;
+        RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b));
+      }
+      gate_done = false;
+      RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      if (n + 1 < ops.size()) {
+        const BackOp& nx = ops[n + 1];
+        CellState& cn = p->cells[nx.k];
+        if (nx.head) RC_TRY(head_back(nx.t));
+        WgGateWork gw;
+        memset(&gw, 0, sizeof(gw));
+        gw.gates = static_cast<const E*>(cn.gates) + static_cast<size_t>(nx.t) * npix * 4 * HP;
+        gw.c_prev = (nx.t == 0) ? nullptr : cn.c + static_cast<size_t>(cslot(cn, nx.t)) * npix * HP;
+        gw.c_next = cn.c + static_cast<size_t>(cslot(cn, nx.t + 1)) * npix * HP;
+        gw.src0 = (nx.t == cn.T - 1) ? nullptr : cn.dh_own;
+        gw.src1 = nx.e1, gw.src2 = nx.e2;
+        gw.dc = cn.dc;
+        gw.dz_out = ctx.dzb[b ^ 1];
+        gw.bias_partial = cn.bpart;
+        gw.npix = static_cast<unsigned>(npix);
+        RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b, &gw));
+        gate_done = true;
+        b ^= 1;
+      } else {
+        RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b));
+      }
+    }
+  } else if (fuse) {
     for (int k = 0; k < ncell; ++k)
       CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0, static_cast<size_t>(kGateGradBlocks) * 4 * HP * 4, st));
     int b = 0;
@@ -1424,7 +1483,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     CU_TRY(cudaEventRecord(ctx.ev_fork, ctx.side));
     CU_TRY(cudaStreamWaitEvent(st, ctx.ev_fork, 0));
   }
-  for (int k = 0; k < ncell; ++k) RC_TRY(cell_finalize(ctx, p->cells[k], grads[2 * k], grads[2 * k + 1], accumulate, st));
+  for (int k = 0; k < ncell; ++k)
+    RC_TRY(cell_finalize(ctx, p->cells[k], grads[2 * k], grads[2 * k + 1], accumulate, st, bias_rows));
   if (grads[2 * ncell]) {
     const int total = c.out_channels * c.hidden * 9;
     head_wgrad_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(p->hpart, grads[2 * ncell], c.out_channels,

@@ -48,10 +48,28 @@ struct WgradParams {
   int dbg_no_tma;  // experiment: after the first ring fill, reuse shared memory (no TMA) -> pure MMA rate
 };
 
-template <typename E>
-__global__ void __launch_bounds__(kWgThreads, 1)
+// Gate-gradient work that can ride along with a wgrad launch (GATE = true): wgrad is tensor bound and leaves the CUDA
+// cores and 50 K of the SM's 64 K registers idle, the gate gradient of the NEXT step of the BPTT chain is an
+// independent HBM stream (its dz goes to the other dz buffer).  16 extra warps per CTA run it as a grid-stride loop
+// over pixels; they share nothing with the GEMM roles (no barrier, no shared memory).
+constexpr int kWgGateThreads = 512;
+struct WgGateWork {
+  const void* gates;     // E [pix][4*HP] of the consumer cell / step
+  const float* c_prev;   // nullable (zeros)
+  const float* c_next;
+  const float* src0;     // dh sources (nullable), fp32 [pix][HP], scaled by S
+  const float* src1;
+  const float* src2;
+  float* dc;             // in/out
+  void* dz_out;          // E [pix][4*HP]
+  float* bias_partial;   // [gridDim.x * 16][4*HP]: one row per worker warp, accumulated
+  unsigned npix;         // HP == 64 and npix * 256 < 2^32 (checked on the host)
+};
+
+template <typename E, bool GATE>
+__global__ void __launch_bounds__(GATE ? kWgThreads + kWgGateThreads : kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
-             const __grid_constant__ CUtensorMap tmB1, const WgradParams p) {
+             const __grid_constant__ CUtensorMap tmB1, const WgradParams p, const WgGateWork gw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -211,7 +229,79 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       umma_commit(done_bar);
     }
-  } else if (warp >= 4) {
+  } else if (GATE && warp >= 8) {
+    // ===================== gate-gradient workers (see WgGateWork) =====================
+    // one item = 1 pixel x 4 channels; a warp covers 2 pixels x 16 chunks; same math as gate_grad_kernel
+    const int wt = threadIdx.x - kWgThreads;
+    const int chunk = wt & 15, plane = wt >> 4;  // 32 pixels per CTA pass
+    const E* gates_c = static_cast<const E*>(gw.gates) + chunk * 4;
+    E* dzo_c = static_cast<E*>(gw.dz_out) + chunk * 4;
+    float bsum[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+    for (unsigned pix = blockIdx.x * 32u + plane; pix < gw.npix; pix += gridDim.x * 32u) {
+      const unsigned o4 = pix * 256u + 0u, o1 = pix * 64u + chunk * 4;
+      uint2 g[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) g[a] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + a * 64));
+      const float4 cp = gw.c_prev ? __ldg(reinterpret_cast<const float4*>(gw.c_prev + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 cn4 = __ldg(reinterpret_cast<const float4*>(gw.c_next + o1));
+      const float4 dc4 = *reinterpret_cast<const float4*>(gw.dc + o1);
+      float dhv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gw.src0) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gw.src0 + o1));
+        dhv[0] += t.x, dhv[1] += t.y, dhv[2] += t.z, dhv[3] += t.w;
+      }
+      if (gw.src1) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gw.src1 + o1));
+        dhv[0] += t.x, dhv[1] += t.y, dhv[2] += t.z, dhv[3] += t.w;
+      }
+      if (gw.src2) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gw.src2 + o1));
+        dhv[0] += t.x, dhv[1] += t.y, dhv[2] += t.z, dhv[3] += t.w;
+      }
+      float gv[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float2 p0 = Elem<E>::unpack2(g[a].x), p1 = Elem<E>::unpack2(g[a].y);
+        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+      }
+      const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+      const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+      const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+      float dzv[4][4], dcn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
+        const float tc = fast_tanh(cnv[e]);
+        const float d_o = dhv[e] * tc;
+        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
+        dzv[0][e] = dct * gg * gi * (1.f - gi);
+        dzv[1][e] = dct * cpv[e] * gf * (1.f - gf);
+        dzv[2][e] = d_o * go * (1.f - go);
+        dzv[3][e] = dct * gi * (1.f - gg * gg);
+        dcn[e] = dct * gf;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
+      }
+      *reinterpret_cast<float4*>(gw.dc + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
+            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+    }
+    // bias partial sums: add the warp's two pixel lanes, one row of bias_partial per worker warp (fixed order)
+    float* row = gw.bias_partial + (static_cast<size_t>(blockIdx.x) * 16 + (warp - 8)) * 256;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = bsum[a][e] + __shfl_xor_sync(0xffffffffu, bsum[a][e], 16);
+        if (lane < 16) row[a * 64 + chunk * 4 + e] += v;
+      }
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     const int row = q * 32 + lane;  // n within the block
     if (my_tiles > 0) {
