@@ -756,20 +756,24 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   const size_t smem = wgrad_smem_bytes(0, 0) + static_cast<size_t>(stages) * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
-    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY(cudaFuncSetAttribute(wgrad_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
     attr_set = true;
   }
   const int groups = (p.total_blocks + p.group_size - 1) / p.group_size;
   const int grid = groups * p.n_blocks * p.splits;
   if (gate != nullptr) {
     if (grid > kBiasRowsMax / 16) return fail(CLSTM_EINVAL, "wgrad + gate workers: grid %d too large", grid);
-    wgrad_kernel<E, true><<<grid, kWgThreads + kWgGateThreads, smem, st>>>(a, b0, b1, p, *gate);
+    if (env_int("CLSTM_WG_GATE", 0) == 2)  // register-rebalanced workers: compiled, not yet run on hardware
+      wgrad_kernel<E, 2><<<grid, kWgThreads + kWgGateThreads2, smem, st>>>(a, b0, b1, p, *gate);
+    else
+      wgrad_kernel<E, 1><<<grid, kWgThreads + kWgGateThreads, smem, st>>>(a, b0, b1, p, *gate);
     return after_launch("wgrad_gate_kernel");
   }
   WgGateWork none;
   memset(&none, 0, sizeof(none));
-  wgrad_kernel<E, false><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p, none);
+  wgrad_kernel<E, 0><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p, none);
   return after_launch("wgrad_kernel");
 }
 

@@ -52,7 +52,8 @@ struct WgradParams {
 // cores and 50 K of the SM's 64 K registers idle, the gate gradient of the NEXT step of the BPTT chain is an
 // independent HBM stream (its dz goes to the other dz buffer).  16 extra warps per CTA run it as a grid-stride loop
 // over pixels; they share nothing with the GEMM roles (no barrier, no shared memory).
-constexpr int kWgGateThreads = 512;
+constexpr int kWgGateThreads = 512;   // GATE == 1: 16 worker warps, <= 80 registers each
+constexpr int kWgGateThreads2 = 384;  // GATE == 2: 12 worker warps with 128 registers each after the rebalance
 struct WgGateWork {
   const void* gates;     // E [pix][4*HP] of the consumer cell / step
   const float* c_prev;   // nullable (zeros)
@@ -66,8 +67,12 @@ struct WgGateWork {
   unsigned npix;         // HP == 64 and npix * 256 < 2^32 (checked on the host)
 };
 
-template <typename E, bool GATE>
-__global__ void __launch_bounds__(GATE ? kWgThreads + kWgGateThreads : kWgThreads, 1)
+// GATE: 0 = plain wgrad (256 threads); 1 = + 16 gate-gradient worker warps, one item in flight per worker (validated,
+// CLSTM_WG_GATE=1); 2 = 12 worker warps after a register rebalance (setmaxnreg: 48 for the GEMM roles, 128 for the
+// workers) with two items in flight per worker.  GATE = 2 compiles but HAS NOT RUN ON HARDWARE YET (CLSTM_WG_GATE=2);
+// it is the first thing to measure next.
+template <typename E, int GATE>
+__global__ void __launch_bounds__(GATE == 2 ? kWgThreads + kWgGateThreads2 : (GATE ? kWgThreads + kWgGateThreads : kWgThreads), 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
              const __grid_constant__ CUtensorMap tmB1, const WgradParams p, const WgGateWork gw) {
   extern __shared__ uint8_t smem_raw[];
@@ -111,10 +116,105 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   // this CTA's K range: pixel tiles split, split+splits, ...
   const int my_tiles = (p.num_p_tiles - split + p.splits - 1) / p.splits;
 
+  // GATE == 2: the register rebalance has to sit at the top of two disjoint code regions (ptxas sizes each region by the
+  // setmaxnreg that dominates it; after a merge it falls back to the launch bound and spills).
+  if (GATE == 2 && warp >= 8) {
+    // launch: 640 threads x 96 registers.  Warps 0-7 (two warpgroups) give back 48 each, the three worker warpgroups
+    // take 32 each: 256 x 48 + 384 x 128 = 61 440 = the launch allocation.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;" ::: "memory");
+    // ===================== gate-gradient workers, two items in flight (NOT YET RUN ON HARDWARE) =====================
+    const int wt = threadIdx.x - kWgThreads;
+    const int chunk = wt & 15, plane = wt >> 4;
+    const E* gates_c = static_cast<const E*>(gw.gates) + chunk * 4;
+    E* dzo_c = static_cast<E*>(gw.dz_out) + chunk * 4;
+    float bsum[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+    struct Raw {
+      uint2 g[4];
+      float4 cp, cn, dc, s0, s1, s2;
+      unsigned pix;
+      bool valid;
+    };
+    auto issue = [&](Raw& r, unsigned pix) {
+      r.pix = pix;
+      r.valid = pix < gw.npix;
+      if (!r.valid) return;
+      const unsigned o4 = pix * 256u, o1 = pix * 64u + chunk * 4;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) r.g[a] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + a * 64));
+      r.cp = gw.c_prev ? __ldg(reinterpret_cast<const float4*>(gw.c_prev + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r.cn = __ldg(reinterpret_cast<const float4*>(gw.c_next + o1));
+      r.dc = *reinterpret_cast<const float4*>(gw.dc + o1);
+      if (gw.src0) r.s0 = __ldg(reinterpret_cast<const float4*>(gw.src0 + o1));
+      if (gw.src1) r.s1 = __ldg(reinterpret_cast<const float4*>(gw.src1 + o1));
+      if (gw.src2) r.s2 = __ldg(reinterpret_cast<const float4*>(gw.src2 + o1));
+    };
+    auto consume = [&](const Raw& r) {
+      float dhv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gw.src0) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
+      if (gw.src1) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
+      if (gw.src2) dhv[0] += r.s2.x, dhv[1] += r.s2.y, dhv[2] += r.s2.z, dhv[3] += r.s2.w;
+      float gv[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float2 p0 = Elem<E>::unpack2(r.g[a].x), p1 = Elem<E>::unpack2(r.g[a].y);
+        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+      }
+      const float cpv[4] = {r.cp.x, r.cp.y, r.cp.z, r.cp.w};
+      const float cnv[4] = {r.cn.x, r.cn.y, r.cn.z, r.cn.w};
+      const float dcv[4] = {r.dc.x, r.dc.y, r.dc.z, r.dc.w};
+      float dzv[4][4], dcn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
+        const float tc = fast_tanh(cnv[e]);
+        const float d_o = dhv[e] * tc;
+        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
+        dzv[0][e] = dct * gg * gi * (1.f - gi);
+        dzv[1][e] = dct * cpv[e] * gf * (1.f - gf);
+        dzv[2][e] = d_o * go * (1.f - go);
+        dzv[3][e] = dct * gi * (1.f - gg * gg);
+        dcn[e] = dct * gf;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
+      }
+      const unsigned o4 = r.pix * 256u, o1 = r.pix * 64u + chunk * 4;
+      *reinterpret_cast<float4*>(gw.dc + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
+            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+    };
+    const unsigned stride = gridDim.x * 24u;  // 384 workers = 24 pixels per CTA pass
+    unsigned p0 = blockIdx.x * 24u + plane, p1 = p0 + stride;
+    Raw ra, rb;
+    issue(ra, p0);
+    issue(rb, p1);
+    while (ra.valid) {
+      consume(ra);
+      p0 += 2 * stride;
+      issue(ra, p0);
+      if (!rb.valid) break;
+      consume(rb);
+      p1 += 2 * stride;
+      issue(rb, p1);
+    }
+    float* row = gw.bias_partial + (static_cast<size_t>(blockIdx.x) * 16 + (warp - 8)) * 256;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = bsum[a][e] + __shfl_xor_sync(0xffffffffu, bsum[a][e], 16);
+        if (lane < 16) row[a * 64 + chunk * 4 + e] += v;
+      }
+  } else {
+  if constexpr (GATE == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
   if (warp == 0) {
     // Lanes 0 .. nblk+1 each own one box of the stage (lane 0/1: the two A boxes, lane 2+j: column block j), so
     // the boxes of a stage are issued in parallel instead of serially by one thread.
@@ -229,7 +329,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       umma_commit(done_bar);
     }
-  } else if (GATE && warp >= 8) {
+  } else if (GATE == 1 && warp >= 8) {
     // ===================== gate-gradient workers (see WgGateWork) =====================
     // one item = 1 pixel x 4 channels; a warp covers 2 pixels x 16 chunks; same math as gate_grad_kernel
     const int wt = threadIdx.x - kWgThreads;
@@ -335,6 +435,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   }
+
+  }  // GEMM roles / GATE == 1 workers
 
   tcgen05_fence_before();
   __syncthreads();
