@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CLSTM_ABI_VERSION 1
+#define CLSTM_ABI_VERSION 2
 
 enum {
   CLSTM_OK = 0,
@@ -105,6 +105,14 @@ int clstm_rollout_forward_layout(clstm_plan_t* plan, const float* x, int x_layou
 int clstm_rollout_backward(clstm_plan_t* plan, const float* dy, const float* y, float* const* grads,
                            int n_grads, int accumulate, void* stream);
 
+/* Range statistics of the last clstm_rollout_backward on this plan, written to DEVICE memory (4 floats, async):
+ *   out4 = { S, 1/S, max |dlogit|, max |S * dz| }
+ * S is the power-of-two loss scale of the 16-bit gradient operands (chosen on the device from max |dlogit|), dz the
+ * gate pre-activation gradients of every cell step (what loss.backward() propagates through conv_lstm.py:176-196).
+ * max |S * dz| = +Inf means a 16-bit operand overflowed (exploding BPTT gradients, or a non-finite dy): the gradients
+ * of that backward are not usable.  The caller decides when to look (satflow_b200 checks it without synchronising). */
+int clstm_plan_grad_status(clstm_plan_t* plan, float* out4, void* stream);
+
 /* Read back a recurrent state in the reference layout (B,hid,H,W) fp32: cell in [0,2L),
  * step in [0,T_cell] where 0 is the zero initial state and T_cell the final state.
  * Either output may be NULL.  In inference plans only the last two c steps are retained. */
@@ -133,11 +141,21 @@ int clstm_cell_plan_create(int batch, int height, int width, int in_channels, in
 int clstm_cell_plan_destroy(clstm_cell_plan_t* plan);
 size_t clstm_cell_plan_workspace_bytes(const clstm_cell_plan_t* plan);
 int clstm_cell_plan_bind(clstm_cell_plan_t* plan, void* workspace, size_t bytes, void* stream);
+/* The same memory as two regions, so that every forward whose backward is still pending can own its activations:
+ *   saved   — written by clstm_cell_forward, read by clstm_cell_backward (packed x / h / c, gates, packed weights);
+ *   scratch — reusable by any later call (loss scale, dz, fp32 dh / dx / dc, split partial sums).
+ * Re-binding is a host-only operation (it re-encodes the tensor maps), so an unrolled sequence — the reference's only
+ * way of using the cell, conv_lstm.py:176-196 — binds a fresh `saved` region per step and keeps it with the autograd
+ * node; clstm_cell_backward must be preceded by a bind of the region its forward wrote. */
+size_t clstm_cell_plan_saved_bytes(const clstm_cell_plan_t* plan);
+size_t clstm_cell_plan_scratch_bytes(const clstm_cell_plan_t* plan);
+int clstm_cell_plan_bind_split(clstm_cell_plan_t* plan, void* saved, size_t saved_bytes, void* scratch,
+                               size_t scratch_bytes, void* stream);
 int clstm_cell_forward(clstm_cell_plan_t* plan, const float* x, const float* h_cur, const float* c_cur,
                        const float* weight, const float* bias, float* h_next, float* c_next, void* stream);
 /* Gradients of one cell step given dL/dh_next, dL/dc_next (either may be NULL == zero).
- * Outputs (any may be NULL): dx, dh_cur, dc_cur, dweight, dbias.  Uses the activations saved by
- * the immediately preceding clstm_cell_forward on this plan. */
+ * Outputs (any may be NULL): dx, dh_cur, dc_cur, dweight, dbias.  Uses the activations that the corresponding
+ * clstm_cell_forward left in the currently bound `saved` region. */
 int clstm_cell_backward(clstm_cell_plan_t* plan, const float* dh_next, const float* dc_next, const float* weight,
                         float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, void* stream);
 
@@ -160,11 +178,6 @@ uint64_t clstm_launch_count(void);
  * timings of clstm_plan_profile_kernel these are taken under the clocks of the real step. */
 int clstm_trace_enable(int capacity);
 long long clstm_trace_report(char* buf, size_t cap);
-
-/* ---- bring-up self tests (device micro-experiments; see tests/test_gpu_selftest.py) -------- */
-/* Shifted shared-memory descriptor experiment: out_max_abs_err is DEVICE memory for
- * n_variants (<= 2) x n_shifts (<= 16) floats, max |D - expected| per (variant, row shift). */
-int clstm_selftest_shifted_desc(float* out_max_abs_err, int n_variants, int n_shifts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,19 +56,22 @@ _PROTOTYPES = {
     "clstm_rollout_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_rollout_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "clstm_rollout_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p]),
+    "clstm_plan_grad_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "clstm_plan_read_state": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "clstm_plan_profile_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "clstm_cell_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "clstm_cell_plan_destroy": (c_int, [c_void_p]),
     "clstm_cell_plan_workspace_bytes": (c_size_t, [c_void_p]),
     "clstm_cell_plan_bind": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "clstm_cell_plan_saved_bytes": (c_size_t, [c_void_p]),
+    "clstm_cell_plan_scratch_bytes": (c_size_t, [c_void_p]),
+    "clstm_cell_plan_bind_split": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "clstm_cell_forward": (c_int, [c_void_p] + [c_void_p] * 7 + [c_void_p]),
     "clstm_cell_backward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_void_p]),
     "clstm_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_launch_count": (c_uint64, []),
     "clstm_trace_enable": (c_int, [c_int]),
     "clstm_trace_report": (ctypes.c_longlong, [ctypes.c_char_p, c_size_t]),
-    "clstm_selftest_shifted_desc": (c_int, [c_void_p, c_int, c_int, c_void_p]),
 }
 
 _lib = None

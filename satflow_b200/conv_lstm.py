@@ -68,6 +68,7 @@ class _RolloutFn(torch.autograd.Function):
         plan.set_weights(params)
         y = plan.forward(x, channels_last=channels_last)
         ctx.plan = plan
+        ctx.generation = plan.generation  # the saved gates / states live in the plan's workspace, not in ctx
         ctx.n_params = len(params)
         ctx.save_for_backward(y, *params)
         return y
@@ -77,7 +78,7 @@ class _RolloutFn(torch.autograd.Function):
         y = ctx.saved_tensors[0]
         params = ctx.saved_tensors[1:]
         grads = [torch.empty_like(p) if ctx.needs_input_grad[3 + i] else None for i, p in enumerate(params)]
-        ctx.plan.backward(dy, y, grads, accumulate=False)
+        ctx.plan.backward(dy, y, grads, accumulate=False, generation=ctx.generation)
         return (None, None, None, *grads)
 
 
@@ -128,14 +129,36 @@ class ConvLSTM(nn.Module):
         else:
             b, seq_len, c, h, w = x.shape
         key = (b, seq_len, c, h, w, forecast_steps, training, self.operand_dtype, x.device.index)
-        plan = self._plans.get(key)
-        if plan is None:
-            if len(self._plans) >= 2:  # bounded: a training plan pins tens of GB
-                self._plans.pop(next(iter(self._plans))).close()
-            plan = RolloutPlan(
+
+        def make():
+            return RolloutPlan(
                 b, h, w, c, self.hidden_dim, self.out_channels, seq_len, forecast_steps, self.n_layers,
                 self.kernel_size, self.operand_dtype, training, 0.0, x.device,
             )
+
+        plan = self._plans.get(key)
+        if plan is not None and plan.pending_backward:
+            # A graph built on this plan has not run its backward yet (two batches summed into one loss, a GAN /
+            # consistency loss, a grad-enabled evaluation pass): its saved states must survive, so this forward gets a
+            # second plan of the same shape.  If that does not fit in HBM the cached plan is reused; the older graph's
+            # backward then raises (generation mismatch) instead of returning gradients of the wrong forward.
+            key2 = key + ("second",)
+            plan2 = self._plans.get(key2)
+            if plan2 is None:
+                try:
+                    plan2 = make()
+                    self._plans[key2] = plan2
+                except torch.OutOfMemoryError:
+                    plan2 = None
+            if plan2 is not None and not plan2.pending_backward:
+                return plan2
+            return plan if plan2 is None or plan.generation <= plan2.generation else plan2
+        if plan is None:
+            # bounded cache (a training plan pins tens of GB); plans with an outstanding backward are never evicted
+            evictable = [k for k, pl in self._plans.items() if not pl.pending_backward]
+            while len(self._plans) >= 3 and evictable:
+                self._plans.pop(evictable.pop(0)).close()
+            plan = make()
             self._plans[key] = plan
         return plan
 
@@ -143,6 +166,18 @@ class ConvLSTM(nn.Module):
         for p in self._plans.values():
             p.close()
         self._plans.clear()
+
+    def check_gradients(self):
+        """Wait for the backwards issued so far and raise ``FloatingPointError`` if a 16-bit gradient operand
+        overflowed in one of them (the same check runs without waiting at the start of every later forward).
+        Returns the range statistics of the newest finished backward (see RolloutPlan.poll_grad_status)."""
+        out = None
+        for p in self._plans.values():
+            if p.training:
+                st = p.poll_grad_status(block=True)
+                if st is not None and (out is None or st["generation"] >= out["generation"]):
+                    out = st
+        return out
 
     # ---- reference API ----------------------------------------------------------------------
     def forward_channels_last(self, x, forecast_steps=0):
@@ -170,6 +205,13 @@ class ConvLSTM(nn.Module):
         plan = self.plan_for(x, int(forecast_steps), training, channels_last)
         if x.dtype != torch.float32:
             x = x.float()
+        if training and x.requires_grad:
+            # the reference's flows never differentiate through the input sequence, and encoder_1's data gradient is not
+            # computed here; returning None silently would be a wrong gradient for whoever asked for it
+            raise RuntimeError(
+                "satflow_b200.ConvLSTM does not produce the gradient w.r.t. its input sequence x; detach() it "
+                "(parameter gradients are unaffected)"
+            )
         return _RolloutFn.apply(plan, x, bool(channels_last), *params)
 
 
@@ -261,7 +303,13 @@ class EncoderDecoderConvLSTM(_Base):
         out = self(x, self.forecast_steps)
         loss, frames = self.loss_and_frame_losses(out, y)
         self.log("train/loss", loss, on_step=True)
-        self.frame_losses = frames.detach()  # device tensor; fetch with one .tolist() when needed
+        # conv_lstm.py:65-69: the reference log_dict()s one python float per frame, each fetched with its own .item()
+        # host sync.  Here the T_out per-frame means come out of the fused loss kernel as ONE device tensor and are
+        # logged as 0-d views of it (Lightning accepts tensors and reduces them over the epoch on the device), so no
+        # synchronisation happens inside the step; ``frame_losses`` keeps the whole vector for a single D2H copy.
+        self.frame_losses = frames.detach()
+        self.log_dict({f"train/frame_{f}_loss": self.frame_losses[f] for f in range(self.frame_losses.shape[0])},
+                      on_step=False, on_epoch=True)
         return loss
 
     def validation_step(self, batch, batch_idx):

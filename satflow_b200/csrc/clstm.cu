@@ -19,12 +19,9 @@
 
 #include "../../include/clstm.h"
 #include "convgemm.cuh"
-#include "convgemm2.cuh"
-#include "convgemm3.cuh"
 #include "dgradT.cuh"
 #include "head_rows.cuh"
 #include "pointwise.cuh"
-#include "selftest.cuh"
 #include "wgrad.cuh"
 
 using namespace clstm;
@@ -86,11 +83,47 @@ inline int after_launch(const char* what) {
   return 0;
 }
 
-// Experiment knobs (read once): integer environment variables, used by tools/kernel_bench.py sweeps.
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+
+// Schedule knobs.  Every setting computes the same function (tests/test_gpu_parity.py::test_alternative_schedules_*
+// keeps each one parity-green); they exist for same-session A/B measurements (tools/ab_fuse.py).  They are read from
+// the environment ONCE, when a plan is created, never at launch time; nothing here can change a result.
+struct Knobs {
+  int stages = kMaxStages;  // CLSTM_STAGES: cap on the operand ring depth of the conv GEMM
+  int rotate = 1;           // CLSTM_ROTATE: per-tile rotated K loop in the conv GEMM
+  int rotate_d = 0;         // CLSTM_ROTATE_D: the same in dgradT (measured: no gain)
+  int staged = 1;           // CLSTM_STAGED: shared-memory staged TMA-store epilogue (0: direct per-thread stores)
+  int dgradT = 1;           // CLSTM_DGRADT: transposed dgrad (0: pixel-major dgrad through convgemm)
+  int fuse_gate = 1;        // CLSTM_FUSE_GATE: gate gradient fused into the dgrad epilogue
+  int fuse_pf = 1;          // CLSTM_FUSE_PF: its L2 prefetch distance in groups
+  int fuse_teams = 2;       // CLSTM_FUSE_TEAMS: its epilogue teams (2 or 4)
+  int head_rows = 1;        // CLSTM_HEAD_ROWS: row-marching output head (0: implicit-GEMM head)
+  int head_band = 32;       // CLSTM_HEAD_BAND: rows per band of the row-marching head
+  int wg_halo = 1;          // CLSTM_WG_HALO: halo-row wgrad
+  int wg_gate = 0;          // CLSTM_WG_GATE: gate gradient on worker warps inside wgrad (1: plain, 2: setmaxnreg)
+  int wg_group = kWgMaxGroupBlocks;  // CLSTM_WG_GROUP: column blocks per wgrad CTA
+  int overlap = 0;          // CLSTM_OVERLAP: wgrad on a side stream
+  void read() {
+    stages = env_int("CLSTM_STAGES", stages);
+    rotate = env_int("CLSTM_ROTATE", rotate);
+    rotate_d = env_int("CLSTM_ROTATE_D", rotate_d);
+    staged = env_int("CLSTM_STAGED", staged);
+    dgradT = env_int("CLSTM_DGRADT", dgradT);
+    fuse_gate = env_int("CLSTM_FUSE_GATE", fuse_gate);
+    fuse_pf = env_int("CLSTM_FUSE_PF", fuse_pf);
+    fuse_teams = env_int("CLSTM_FUSE_TEAMS", fuse_teams);
+    head_rows = env_int("CLSTM_HEAD_ROWS", head_rows);
+    head_band = env_int("CLSTM_HEAD_BAND", head_band);
+    wg_halo = env_int("CLSTM_WG_HALO", wg_halo);
+    wg_gate = env_int("CLSTM_WG_GATE", wg_gate);
+    wg_group = env_int("CLSTM_WG_GROUP", wg_group);
+    if (wg_group < 1 || wg_group > kWgMaxGroupBlocks) wg_group = kWgMaxGroupBlocks;
+    overlap = env_int("CLSTM_OVERLAP", overlap);
+  }
+};
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -177,14 +210,6 @@ int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, i
   return 0;
 }
 
-// The weight tile of a stage is fetched as this many TMA boxes (issued by different lanes).
-inline int weight_boxes(int n_tile) {
-  // Measured: splitting the weight tile into 4 boxes slows the conv GEMMs (fwd 404 -> 427 us without epilogue,
-  // dgrad 673 -> 890 us); one box issued by its own lane (parallel with the A box) is best.
-  const int v = env_int("CLSTM_B_BOXES", 1);
-  return (v == 1 || v == 2 || v == 4) && n_tile % (8 * v) == 0 ? v : 1;
-}
-
 // fp32 [N][H][W][C] tensor written in [16 px along W] x 64-channel boxes (256-byte rows, no swizzle): the
 // transposed dgrad's output blocks.
 int make_map_out64(CUtensorMap* m, const void* ptr, int C, int W, int H, long long N) {
@@ -261,15 +286,13 @@ struct Ctx {
   void* dzb[2] = {nullptr, nullptr};  // two dz buffers: gate-grad of step n+1 overlaps the wgrad of step n
   float* scale = nullptr;  // device {S, 1/S}
   unsigned int* amax = nullptr;
-  CUtensorMap m_dz128, m_dz64, m_dzhalo;
-  CUtensorMap m_dz128b[2], m_dz64b[2], m_dzhalob[2];
-  CUtensorMap m_dzrow256[2], m_dzrow8[2];  // halo-row dgradT: 256-pixel and 8-pixel single-row boxes
-  bool rows_ok = false;
+  Knobs knobs;
+  CUtensorMap m_dz128, m_dz64;
+  CUtensorMap m_dz128b[2], m_dz64b[2];
   cudaStream_t side = nullptr;                    // weight-gradient stream (created at bind)
   cudaEvent_t ev_d[2] = {nullptr, nullptr};       // dgrad of the step using buffer i has been enqueued/finished
   cudaEvent_t ev_w[2] = {nullptr, nullptr};       // wgrad has finished reading buffer i
   cudaEvent_t ev_fork = nullptr;
-  bool pair_ok = false;  // geometry allows the CTA-pair halo kernel (one-row 128-pixel tiles)
 };
 
 struct CellState {
@@ -281,8 +304,6 @@ struct CellState {
   int with_x = 0;
   int n_tile_d = 0;
   int slots_h = 0, slots_c = 0;
-  int h_stride = 1, c_stride = 1;  // slot permutation strides (coprime with the slot counts)
-  int h_rot = 0;                   // per-cell rotation of the h slots (full stacks only)
   int wg_total = 0, wg_group = 0, wg_splits = 0;
   bool bwd_started = false;
   // packed parameters
@@ -299,13 +320,10 @@ struct CellState {
   float* dc = nullptr;      // fp32 [npix][HP]
   float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
-  CUtensorMap m_h128, m_h64, m_hhalo, m_hhalo3, m_wp, m_wd, m_wp_half, m_wd_half;
-  CUtensorMap m_wp32, m_wd32;                       // 32-row weight boxes (two-row halo kernel)
+  CUtensorMap m_h128, m_h64, m_wp, m_wd;
   CUtensorMap m_h66;                                // wgrad halo rows: box 64 ch x 66 px x 1 row
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
-  CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue
-  std::vector<CUtensorMap> m_c16s, m_h16s, m_g16s;   // the same, one map per slot / step (N = B images, offset 0)
-  std::vector<CUtensorMap> m_h128s;                  // per-slot A-operand load maps (experiment) (staged store / c_prev load) maps
+  CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
 };
@@ -315,7 +333,6 @@ struct InputRef {
   const CUtensorMap* map128 = nullptr;
   const CUtensorMap* map64 = nullptr;
   const CUtensorMap* map66 = nullptr;    // wgrad halo rows (conv inputs only)
-  const CUtensorMap* maphalo = nullptr;  // one-row halo boxes (pair kernel); == map128 for direct inputs
   int b_off = 0;  // image offset (slot * B)
 };
 
@@ -331,10 +348,8 @@ struct Carver {
   }
 };
 
-void wgrad_shape(const DeviceInfo& dev, int total_blocks, int n_blocks, long long p_tiles, int* group_size,
-                 int* splits) {
-  int max_group = env_int("CLSTM_WG_GROUP", kWgMaxGroupBlocks);
-  if (max_group < 1 || max_group > kWgMaxGroupBlocks) max_group = kWgMaxGroupBlocks;
+void wgrad_shape(const DeviceInfo& dev, int max_group, int total_blocks, int n_blocks, long long p_tiles,
+                 int* group_size, int* splits) {
   int groups = (total_blocks + max_group - 1) / max_group;
   int gs = (total_blocks + groups - 1) / groups;
   groups = (total_blocks + gs - 1) / gs;
@@ -362,24 +377,27 @@ void init_cell(CellState* cs, const Ctx& ctx, int cin, int hid, int kh, int kw, 
   cs->n_tile_d = nt;
   cs->wg_total = cs->Kf / 64;
   const long long p_tiles = static_cast<long long>(ctx.geo.B) * ctx.geo.tiles_w2 * ctx.geo.tiles_h2;
-  wgrad_shape(ctx.dev, cs->wg_total, 4 * g.HP / 128, p_tiles, &cs->wg_group, &cs->wg_splits);
+  wgrad_shape(ctx.dev, ctx.knobs.wg_group, cs->wg_total, 4 * g.HP / 128, p_tiles, &cs->wg_group, &cs->wg_splits);
 }
 
-void carve_cell(Carver& cv, CellState& cs, const Ctx& ctx) {
+// `sv` receives what a backward needs from the forward (packed weights, state stacks, gates), `sc` the scratch that
+// any later call may overwrite.  A rollout plan passes the same carver twice (one workspace); a cell plan keeps the
+// two apart so that every autograd node can own its saved region (clstm_cell_plan_bind_split).
+void carve_cell(Carver& sv, Carver& sc, CellState& cs, const Ctx& ctx) {
   const size_t npix = ctx.geo.npix();
   const int HP = ctx.HP;
-  cs.wp = cv.take<void>(static_cast<size_t>(4 * HP) * cs.Kf * 2);
-  cs.bias_p = cv.take<float>(static_cast<size_t>(4 * HP) * 4);
-  cs.h = cv.take<void>(static_cast<size_t>(cs.slots_h) * npix * HP * 2);
-  cs.c = cv.take<float>(static_cast<size_t>(cs.slots_c) * npix * HP * 4);
+  cs.wp = sv.take<void>(static_cast<size_t>(4 * HP) * cs.Kf * 2);
+  cs.bias_p = sv.take<float>(static_cast<size_t>(4 * HP) * 4);
+  cs.h = sv.take<void>(static_cast<size_t>(cs.slots_h) * npix * HP * 2);
+  cs.c = sv.take<float>(static_cast<size_t>(cs.slots_c) * npix * HP * 4);
   if (ctx.training) {
-    cs.wd = cv.take<void>(static_cast<size_t>(cs.rows_d) * cs.Kd * 2);
-    cs.gates = cv.take<void>(static_cast<size_t>(cs.T) * npix * 4 * HP * 2);
-    cs.dh_own = cv.take<float>(npix * HP * 4);
-    cs.dxb = cs.with_x ? cv.take<float>(npix * cs.g.CIP * 4) : nullptr;
-    cs.dc = cv.take<float>(npix * HP * 4);
-    cs.wpart = cv.take<float>(static_cast<size_t>(cs.wg_splits) * 4 * HP * cs.Kf * 4);
-    cs.bpart = cv.take<float>(static_cast<size_t>(kBiasRowsMax) * 4 * HP * 4);
+    cs.wd = sv.take<void>(static_cast<size_t>(cs.rows_d) * cs.Kd * 2);
+    cs.gates = sv.take<void>(static_cast<size_t>(cs.T) * npix * 4 * HP * 2);
+    cs.dh_own = sc.take<float>(npix * HP * 4);
+    cs.dxb = cs.with_x ? sc.take<float>(npix * cs.g.CIP * 4) : nullptr;
+    cs.dc = sc.take<float>(npix * HP * 4);
+    cs.wpart = sc.take<float>(static_cast<size_t>(cs.wg_splits) * 4 * HP * cs.Kf * 4);
+    cs.bpart = sc.take<float>(static_cast<size_t>(kBiasRowsMax) * 4 * HP * 4);
   }
 }
 
@@ -389,9 +407,9 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_act(&cs.m_h128, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
   RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
   if (g.BW2 == 64 && g.BH2 == 1) RC_TRY(make_map_act(&cs.m_h66, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 66, 1));
-  RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256 / weight_boxes(256)));
+  RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256));
   if (ctx.training)
-    RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / weight_boxes(cs.n_tile_d)));
+    RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
                       g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
@@ -404,73 +422,31 @@ int map_cell(CellState& cs, const Ctx& ctx) {
     if (cs.with_x) RC_TRY(make_map_out64(&cs.m_dxT, cs.dxb, cs.g.CIP, g.W, g.H, g.B));
     if (cs.with_x) RC_TRY(make_map_epi(&cs.m_dx16, 4, ctx.dtype, cs.dxb, cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
   }
-  if (env_int("CLSTM_SLOT_MAPS", 0)) {
-    // One store map per slot: measured 35 us faster per cell step than one map over the whole stack with an image
-    // offset (finding 2).
-    const size_t npix = g.npix();
-    cs.m_h16s.resize(cs.slots_h);
-    for (int sl = 0; sl < cs.slots_h; ++sl)
-      RC_TRY(make_map_epi(&cs.m_h16s[sl], 2, ctx.dtype, static_cast<uint8_t*>(cs.h) + static_cast<size_t>(sl) * npix * ctx.HP * 2,
-                          ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
-    cs.m_h128s.resize(cs.slots_h);
-    for (int sl = 0; sl < cs.slots_h; ++sl)
-      RC_TRY(make_map_act(&cs.m_h128s[sl], ctx.dtype, static_cast<uint8_t*>(cs.h) + static_cast<size_t>(sl) * npix * ctx.HP * 2,
-                          ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
-    cs.m_c16s.resize(cs.slots_c);
-    for (int sl = 0; sl < cs.slots_c; ++sl)
-      RC_TRY(make_map_epi(&cs.m_c16s[sl], 4, ctx.dtype, cs.c + static_cast<size_t>(sl) * npix * ctx.HP, ctx.HP, g.W, g.H,
-                          g.B, g.BW, g.BH));
-    if (ctx.training) {
-      cs.m_g16s.resize(cs.T);
-      for (int t = 0; t < cs.T; ++t)
-        RC_TRY(make_map_epi(&cs.m_g16s[t], 2, ctx.dtype,
-                            static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * ctx.HP * 2, 4 * ctx.HP,
-                            g.W, g.H, g.B, g.BW, g.BH));
-    }
-  }
-  if (ctx.pair_ok) {
-    RC_TRY(make_map_act(&cs.m_hhalo, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 128 + cs.g.kw - 1, 1));
-    RC_TRY(make_map_act(&cs.m_hhalo3, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 130, 1));  // the head's 3x3 conv
-    RC_TRY(make_map_w(&cs.m_wp_half, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
-    RC_TRY(make_map_w(&cs.m_wp32, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 32));
-    if (ctx.training) RC_TRY(make_map_w(&cs.m_wd32, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, 32));
-    if (ctx.training) RC_TRY(make_map_w(&cs.m_wd_half, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d / 2));
-  }
   return 0;
 }
 
 // --------------------------------------------------------------------------- launch helpers
 template <typename E, int EPI>
-int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+int launch_convgemm(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                     ConvGemmParams p, const Geo& g, long long images, cudaStream_t st,
                     const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr,
                     const CUtensorMap* x3 = nullptr) {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
-  // staged epilogue: 0 = direct per-thread stores, 1 = TMA stores, 2 = cooperative coalesced stores (EPI_LSTM)
-  p.staged = (x0 != nullptr && EPI != EPI_HEAD) ? (env_int("CLSTM_STAGED", 1) ? 1 : 0) : 0;
-  p.b_boxes = weight_boxes(p.n_tile);
-  p.prod_serial = env_int("CLSTM_PROD_SERIAL", 0);
-  p.dbg_no_tma = env_int("CLSTM_NOTMA", 0);
-  p.hint_store = env_int("CLSTM_HINT_STORE", 0);
-  p.hint_w = env_int("CLSTM_HINT_W", 0);
-  p.hint_a = env_int("CLSTM_HINT_A", 0);
-  if (EPI == EPI_STORE) p.skip_mask = env_int("CLSTM_SKIP", 0);
+  const DeviceInfo& dev = cx.dev;
+  // staged epilogue: outputs go through swizzled shared memory + TMA stores (0: direct per-thread stores)
+  p.staged = (x0 != nullptr && EPI != EPI_HEAD && cx.knobs.staged) ? 1 : 0;
   {
     int kblocks = 0;
     for (int s = 0; s < p.nseg; ++s) kblocks += p.seg[s].chunks * p.seg[s].kh * p.seg[s].kw;
-    p.rotate = (kblocks <= kKtabMax && kblocks > 1 && !p.dbg_no_tma && !p.prod_serial && p.b_boxes == 1 && !p.hint_a &&
-                !p.hint_w && env_int("CLSTM_ROTATE", 1))
-                   ? 1
-                   : 0;
+    p.rotate = (kblocks <= kKtabMax && kblocks > 1 && cx.knobs.rotate) ? 1 : 0;
   }
   const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));
   int stages = (dev.smem_optin - fixed) / stage_bytes;
-  const int max_stages = env_int("CLSTM_STAGES", kMaxStages);
-  if (stages > max_stages) stages = max_stages;
+  if (stages > cx.knobs.stages) stages = cx.knobs.stages;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(CLSTM_EINVAL, "convgemm: not enough shared memory for n_tile=%d", p.n_tile);
   p.stages = stages;
@@ -488,123 +464,14 @@ int launch_convgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensor
   return after_launch("convgemm_kernel");
 }
 
-// CTA-pair, halo-stationary variant (convgemm2.cuh).  `a0/a1` must be one-row halo maps (box 128 + kw - 1)
-// for conv segments and plain 128-pixel maps for direct segments; `b` a half-tile weight map.
-template <typename E, int EPI>
-int launch_pairgemm(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                    ConvGemmParams p, const Geo& g, long long images, cudaStream_t st, bool* used) {
-  *used = false;
-  if (g.BW != 128 || g.BH != 1 || !env_int("CLSTM_PAIR", 0)) return 0;
-  PairGemmParams pp;
-  memset(&pp, 0, sizeof(pp));
-  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
-  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
-  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
-  int slot = 0;
-  pp.halo = env_int("CLSTM_PAIR_HALO", 1);
-  for (int s = 0; s < p.nseg; ++s) {
-    pp.halo_w[s] = 128 + p.seg[s].kw - 1;
-    pp.pitch[s] = round_up(pp.halo_w[s], 8);
-    const int bytes = pp.halo ? p.seg[s].kh * pp.pitch[s] * 128 : kABytes;
-    if (bytes > slot) slot = bytes;
-  }
-  pp.a_slot_bytes = slot;
-  pp.a_stages = env_int("CLSTM_PAIR_ASTAGES", pp.halo ? 2 : 4);
-  if (pp.a_stages < 1 || pp.a_stages > kPairMaxAStages) pp.a_stages = 2;
-  const int b_stage = (p.n_tile / 2) * 128;
-  const long long fixed = static_cast<long long>(pairgemm_smem_bytes(pp.a_stages, slot, 0, p.n_tile, p.n_tiles));
-  long long bs = (dev.smem_optin - fixed) / b_stage;
-  if (bs > kPairMaxBStages) bs = kPairMaxBStages;
-  if (bs < 2) return 0;  // does not fit (large kernels): caller falls back to the per-tap kernel
-  pp.b_stages = static_cast<int>(bs);
-  pp.g = p;
-  const size_t smem = pairgemm_smem_bytes(pp.a_stages, slot, pp.b_stages, p.n_tile, p.n_tiles);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(pairgemm_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                dev.smem_optin));
-    attr_set = true;
-  }
-  const int units = ((p.num_m_tiles + 1) / 2) * p.n_tiles;
-  int clusters = dev.sms / 2;
-  if (clusters > units) clusters = units;
-  pairgemm_kernel<E, EPI><<<2 * clusters, kGemmThreads, smem, st>>>(a0, a1, b, pp);
-  *used = true;
-  return after_launch("pairgemm_kernel");
-}
-
-// Two-row halo kernel (convgemm3.cuh).  a0/a1: one-row maps (box 128 + kw - 1 for conv segments, 128 for direct
-// ones); b: 32-row weight boxes; x0..x2: the staged-epilogue maps.
-template <typename E, int EPI>
-int launch_halo2(const DeviceInfo& dev, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                 const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& x2, ConvGemmParams p, const Geo& g,
-                 long long images, cudaStream_t st, bool* used) {
-  *used = false;
-  if (g.BW != 128 || g.BH != 1 || !env_int("CLSTM_HALO2", 1)) return 0;
-  const int n_total = p.n_tiles * p.n_tile;
-  if (EPI == EPI_LSTM && p.n_tile != 256) return 0;
-  if (EPI == EPI_HEAD) {
-    if (n_total > 32) return 0;  // one weight box of <= 32 rows
-  } else if (n_total % 64) {
-    return 0;
-  }
-  Halo2Params hp;
-  memset(&hp, 0, sizeof(hp));
-  p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
-  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
-  p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
-  p.staged = (EPI == EPI_HEAD) ? 0 : 1;
-  hp.n_sub = (EPI == EPI_LSTM) ? 128 : (EPI == EPI_HEAD ? n_total : ((n_total % 128 == 0) ? 128 : 64));
-  hp.n_subs = n_total / hp.n_sub;
-  hp.row_pairs = (g.H + 1) / 2;
-  int slot = 0, max_kh = 1;
-  for (int s = 0; s < p.nseg; ++s) {
-    hp.halo_w[s] = 128 + p.seg[s].kw - 1;
-    hp.pitch[s] = round_up(hp.halo_w[s], 8);
-    if (hp.pitch[s] * 128 > slot) slot = hp.pitch[s] * 128;
-    if (p.seg[s].kh > max_kh) max_kh = p.seg[s].kh;
-  }
-  hp.a_row_bytes = slot;
-  const int stg = h2_stg_bytes(EPI);
-  const int bias_floats = p.bias ? n_total : 0;
-  // shared-memory split: at least kh + 3 ring rows and 4 weight stages, then alternate extra stages / rows
-  int rows = max_kh + 3, bst = env_int("CLSTM_H2_BSTAGES", 4);
-  auto fits = [&](int r, int bs) {
-    return halo2_smem_bytes(r, slot, bs, hp.n_sub, stg, bias_floats) <= static_cast<size_t>(dev.smem_optin);
-  };
-  if (!fits(rows, bst)) {
-    rows = max_kh + 2;
-    if (!fits(rows, bst)) return 0;
-  }
-  bool grew = true;
-  while (grew) {
-    grew = false;
-    if (rows < kH2MaxRows && rows < 2 * (max_kh + 1) + 1 && fits(rows + 1, bst)) ++rows, grew = true;
-    if (bst < kH2MaxBStages && fits(rows, bst + 1)) ++bst, grew = true;
-  }
-  hp.a_rows = rows;
-  hp.b_stages = bst;
-  hp.g = p;
-  const size_t smem = halo2_smem_bytes(rows, slot, bst, hp.n_sub, stg, bias_floats);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(halo2_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
-    attr_set = true;
-  }
-  const long long units = static_cast<long long>(images) * hp.row_pairs * g.tiles_w * hp.n_subs;
-  const int grid = units < dev.sms ? static_cast<int>(units) : dev.sms;
-  halo2_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0, x1, x2, hp);
-  *used = true;
-  return after_launch("halo2_kernel");
-}
-
 // Transposed dgrad (dgradT.cuh): channels as M, 256 pixels as N.
 template <typename E>
-int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
+int launch_dgradT(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
                   const CUtensorMap& x1, const ConvSeg& seg, int rows_d, int split_col, const Geo& g, long long images,
                   cudaStream_t st, bool* used) {
   *used = false;
-  if (g.BW < 16 || !env_int("CLSTM_DGRADT", 1)) return 0;
+  const DeviceInfo& dev = cx.dev;
+  if (g.BW < 16 || !cx.knobs.dgradT) return 0;
   DgradTParams p;
   memset(&p, 0, sizeof(p));
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
@@ -615,7 +482,7 @@ int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtenso
   p.split_col = split_col;
   p.lbw = 0;
   while ((1 << p.lbw) < g.BW) ++p.lbw;
-  p.rotate = env_int("CLSTM_ROTATE_D", 0) ? 1 : 0;  // measured: no gain for dgrad (weights are 1/3 of its operand bytes)
+  p.rotate = cx.knobs.rotate_d ? 1 : 0;  // measured: no gain for dgrad (weights are 1/3 of its operand bytes)
   int stages = (dev.smem_optin - static_cast<int>(dgradT_smem_bytes(0))) / kDtStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return 0;
@@ -634,8 +501,9 @@ int launch_dgradT(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtenso
 
 // Transposed dgrad whose epilogue also runs the gate gradient of the NEXT cell step of the backward chain.
 template <typename E>
-int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x1,
+int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x1,
                         const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f, cudaStream_t st) {
+  const DeviceInfo& dev = cx.dev;
   DgradTParams p;
   memset(&p, 0, sizeof(p));
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
@@ -645,7 +513,7 @@ int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const C
   p.m_tiles = 1;
   p.lbw = 0;
   while ((1 << p.lbw) < g.BW) ++p.lbw;
-  p.rotate = env_int("CLSTM_ROTATE_D", 0) ? 1 : 0;  // measured: no gain for dgrad (weights are 1/3 of its operand bytes)
+  p.rotate = cx.knobs.rotate_d ? 1 : 0;
   int stages = (dev.smem_optin - static_cast<int>(dgradTf_smem_bytes(0))) / kDtStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(CLSTM_EINVAL, "dgradT_fused: not enough shared memory");
@@ -658,7 +526,7 @@ int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const C
     CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
     attr_set = true;
   }
-  if (env_int("CLSTM_FUSE_TEAMS", 2) == 4)
+  if (cx.knobs.fuse_teams == 4)
     dgradT_fused_kernel<E, 4><<<grid, 128 + 4 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
   else
     dgradT_fused_kernel<E, 2><<<grid, 128 + 2 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
@@ -668,17 +536,18 @@ int launch_dgradT_fused(const DeviceInfo& dev, const CUtensorMap& dz128, const C
 // Row-marching output head (head_rows.cuh).  `used` stays false when the shape is not supported (the caller then
 // runs the implicit-GEMM head).
 template <typename E>
-int launch_head_rows(const DeviceInfo& dev, const CUtensorMap& h128, const CUtensorMap& wz, HeadRowsParams p,
+int launch_head_rows(const Ctx& cx, const CUtensorMap& h128, const CUtensorMap& wz, HeadRowsParams p,
                      const Geo& g, cudaStream_t st, bool* used) {
   *used = false;
-  if (g.BW != 128 || g.BH != 1 || p.c_out > 16 || !env_int("CLSTM_HEAD_ROWS", 1)) return 0;
+  const DeviceInfo& dev = cx.dev;
+  if (g.BW != 128 || g.BH != 1 || p.c_out > 16 || !cx.knobs.head_rows) return 0;
   p.H = g.H, p.W = g.W;
   if (g.W <= 256) {
     p.strips = 1, p.strip_w = 256, p.x_halo = 0;
   } else {
     p.strip_w = 254, p.x_halo = 1, p.strips = (g.W + 253) / 254;
   }
-  p.band_rows = env_int("CLSTM_HEAD_BAND", 32);
+  p.band_rows = cx.knobs.head_band > 0 ? cx.knobs.head_band : 32;
   p.bands = (g.H + p.band_rows - 1) / p.band_rows;
   int stages = (dev.smem_optin - static_cast<int>(head_rows_smem_bytes(p.chunks, 0))) / kABytes;
   if (stages > kHrMaxStages) stages = kHrMaxStages;
@@ -710,40 +579,10 @@ int launch_head_rows(const DeviceInfo& dev, const CUtensorMap& h128, const CUten
   return after_launch("head_rows_kernel");
 }
 
-// Halo-row transposed dgrad (3x3, W > 128).
 template <typename E>
-int launch_dgradT_halo(const DeviceInfo& dev, const CUtensorMap& row256, const CUtensorMap& row8, const CUtensorMap& wT,
-                       const CUtensorMap& x0, const CUtensorMap& x1, const ConvSeg& seg, int rows_d, int split_col,
-                       const Geo& g, cudaStream_t st, bool* used) {
-  *used = false;
-  if (seg.kh != 3 || seg.kw != 3 || g.W <= 128 || !env_int("CLSTM_DGRADT_HALO", 0)) return 0;
-  DgradTHaloParams p;
-  memset(&p, 0, sizeof(p));
-  p.B = g.B, p.H = g.H, p.W = g.W;
-  p.segs_w = (g.W + 255) / 256;
-  p.chunks = seg.chunks;
-  p.m_tiles = (rows_d + 127) / 128;
-  p.split_col = split_col;
-  p.rows = 4;
-  p.w_stages = 4;
-  while (p.w_stages < kMaxStages && dgradTh_smem_bytes(p.w_stages + 1, p.rows) <= static_cast<size_t>(dev.smem_optin))
-    ++p.w_stages;
-  if (dgradTh_smem_bytes(p.w_stages, p.rows) > static_cast<size_t>(dev.smem_optin)) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(dgradT_halo_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
-    attr_set = true;
-  }
-  const long long units = static_cast<long long>(g.B) * g.H * p.segs_w * p.m_tiles;
-  const int grid = units < dev.sms ? static_cast<int>(units) : dev.sms;
-  dgradT_halo_kernel<E><<<grid, kGemmThreads, dgradTh_smem_bytes(p.w_stages, p.rows), st>>>(row256, row8, wT, x0, x1, p);
-  *used = true;
-  return after_launch("dgradT_halo_kernel");
-}
-
-template <typename E>
-int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
+int launch_wgrad(const Ctx& cx, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
                  WgradParams p, const Geo& g, long long images, cudaStream_t st, const WgGateWork* gate = nullptr) {
+  const DeviceInfo& dev = cx.dev;
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW2, p.BH = g.BH2, p.tiles_w = g.tiles_w2, p.tiles_h = g.tiles_h2;
   p.num_p_tiles = static_cast<int>(images) * g.tiles_w2 * g.tiles_h2;
@@ -752,7 +591,6 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(CLSTM_EINVAL, "wgrad: not enough shared memory");
   p.stages = stages;
-  p.dbg_no_tma = env_int("CLSTM_WG_NOTMA", 0);
   const size_t smem = wgrad_smem_bytes(0, 0) + static_cast<size_t>(stages) * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
@@ -765,7 +603,7 @@ int launch_wgrad(const DeviceInfo& dev, const CUtensorMap& a, const CUtensorMap&
   const int grid = groups * p.n_blocks * p.splits;
   if (gate != nullptr) {
     if (grid > kBiasRowsMax / 16) return fail(CLSTM_EINVAL, "wgrad + gate workers: grid %d too large", grid);
-    if (env_int("CLSTM_WG_GATE", 0) == 2)  // register-rebalanced workers: compiled, not yet run on hardware
+    if (cx.knobs.wg_gate == 2)  // register-rebalanced workers
       wgrad_kernel<E, 2><<<grid, kWgThreads + kWgGateThreads2, smem, st>>>(a, b0, b1, p, *gate);
     else
       wgrad_kernel<E, 1><<<grid, kWgThreads + kWgGateThreads, smem, st>>>(a, b0, b1, p, *gate);
@@ -830,54 +668,15 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.h_next = static_cast<E*>(cs.h) + static_cast<size_t>(sn) * cs.h_slot_elems(ctx.geo);
   p.gates = gates;
   p.ldc = ctx.HP;
-  p.act_mode = env_int("CLSTM_ACT_MODE", 3);
-  p.skip_mask = env_int("CLSTM_SKIP", 0);
-  p.lsu_mask = env_int("CLSTM_LSU", 0);
-  if (ctx.pair_ok && !(g.in_col && env_int("CLSTM_PAIR", 0) == 2)) {  // CLSTM_PAIR=2: not for the xcol cell
-    bool used = false;
-    const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
-    RC_TRY((launch_pairgemm<E, EPI_LSTM>(ctx.dev, halo ? *in.maphalo : *in.map128, halo ? cs.m_hhalo : cs.m_h128,
-                                         cs.m_wp_half, p, ctx.geo, ctx.geo.B, st, &used)));
-    if (used) return 0;
-  }
   if (cnext_slot >= 0) {  // staged epilogue: image offsets into the c / h / gates stacks
     p.cprev_boff = (c_prev != nullptr && cprev_slot >= 0) ? cprev_slot * ctx.geo.B : -1;
     p.cnext_boff = cnext_slot * ctx.geo.B;
     p.hnext_boff = sn * ctx.geo.B;
     p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
-    if (ctx.pair_ok && env_int("CLSTM_HALO2_FWD", 0)) {
-      bool used = false;
-      RC_TRY((launch_halo2<E, EPI_LSTM>(ctx.dev, *in.maphalo, cs.m_hhalo, cs.m_wp32, cs.m_c16, cs.m_h16,
-                                        ctx.training ? cs.m_g16 : cs.m_h16, p, ctx.geo, ctx.geo.B, st, &used)));
-      if (used) return 0;
-    }
-    if (!cs.m_h16s.empty()) {  // per-slot epilogue maps: every image offset becomes 0
-      const CUtensorMap* mcp = &cs.m_c16s[cnext_slot];
-      if (p.cprev_boff >= 0) {
-        mcp = &cs.m_c16s[cprev_slot];
-        p.cprev_boff = 0;
-      }
-      const CUtensorMap* mc = &cs.m_c16s[cnext_slot];
-      p.cnext_boff = 0;
-      const CUtensorMap* mh = &cs.m_h16s[sn];
-      p.hnext_boff = 0;
-      const CUtensorMap* mg = mh;
-      if (p.gates_boff >= 0) {
-        mg = &cs.m_g16s[gates_step];
-        p.gates_boff = 0;
-      }
-      if (env_int("CLSTM_SLOT_MAPS", 0) >= 2) {  // also read own h_prev through a per-slot map
-        p.seg[1].b_off = 0;
-        return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128s[sp], cs.m_wp, p, ctx.geo, ctx.geo.B, st, mc, mh,
-                                            mg, mcp);
-      }
-      return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, mc, mh, mg,
-                                          mcp);
-    }
-    return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
+    return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
                                         &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16);
   }
-  return launch_convgemm<E, EPI_LSTM>(ctx.dev, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
+  return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
 }
 
 // Backward of one cell step, three launches: fused gate gradient -> dgrad (dx | dh_prev) -> wgrad
@@ -890,7 +689,7 @@ int cell_gate_grad(const Ctx& ctx, CellState& cs, const void* gates, const float
   // two kernels still did not overlap: DESIGN.md "backward overlap".)
   gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 9 * sizeof(float), st>>>(
       static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dzb[buf]), cs.bpart,
-      !first, ctx.geo.npix(), ctx.HP);
+      !first, ctx.geo.npix(), ctx.HP, ctx.amax + 1);
   return after_launch("gate_grad_kernel");
 }
 
@@ -910,40 +709,19 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
   p.ld0 = g.CIP;
   p.ld1 = ctx.HP;
   p.out_scale = 1.f;
-  if (ctx.rows_ok) {
-    bool used = false;
-    RC_TRY((launch_dgradT_halo<E>(ctx.dev, ctx.m_dzrow256[buf], ctx.m_dzrow8[buf], cs.m_wdT,
-                                  cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0], cs.rows_d, p.split_col, ctx.geo, st,
-                                  &used)));
-    if (used) return 0;
-  }
   {
     bool used = false;
-    RC_TRY((launch_dgradT<E>(ctx.dev, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
+    RC_TRY((launch_dgradT<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT, p.seg[0],
                              cs.rows_d, p.split_col, ctx.geo, ctx.geo.B, st, &used)));
     if (used) return 0;
   }
-  if (ctx.pair_ok && env_int("CLSTM_HALO2_DGRAD", 0)) {
-    bool used = false;
-    RC_TRY((launch_halo2<E, EPI_STORE>(ctx.dev, ctx.m_dzhalob[buf], ctx.m_dzhalob[buf], cs.m_wd32, cs.with_x ? cs.m_dx16 : cs.m_dh16,
-                                       cs.m_dh16, cs.m_dh16, p, ctx.geo, ctx.geo.B, st, &used)));
-    if (used) return 0;
-  }
-  if (ctx.pair_ok) {
-    bool used = false;
-    const bool halo = env_int("CLSTM_PAIR_HALO", 1) != 0;
-    RC_TRY((launch_pairgemm<E, EPI_STORE>(ctx.dev, halo ? ctx.m_dzhalob[buf] : ctx.m_dz128b[buf],
-                                          halo ? ctx.m_dzhalob[buf] : ctx.m_dz128b[buf],
-                                          cs.m_wd_half, p, ctx.geo, ctx.geo.B, st, &used)));
-    if (used) return 0;
-  }
-  return launch_convgemm<E, EPI_STORE>(ctx.dev, ctx.m_dz128b[buf], ctx.m_dz128b[buf], cs.m_wd, p, ctx.geo, ctx.geo.B, st,
+  return launch_convgemm<E, EPI_STORE>(ctx, ctx.m_dz128b[buf], ctx.m_dz128b[buf], cs.m_wd, p, ctx.geo, ctx.geo.B, st,
                                        cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16);
 }
 
-// slot of a cell's h / c state after `s` steps (s = 0: initial zeros); see pick_stride for the permutation
-inline int hslot(const CellState& cs, int s) { return ((s % cs.slots_h) * cs.h_stride + cs.h_rot) % cs.slots_h; }
-inline int cslot(const CellState& cs, int s) { return (s % cs.slots_c) * cs.c_stride % cs.slots_c; }
+// slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
+inline int hslot(const CellState& cs, int s) { return s % cs.slots_h; }
+inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
 
 // dgrad of `cs` (reading dz[buf]) with the gate gradient of the NEXT step of the backward chain — cell `cn`, time
 // step `nt`, dh sources own / e1 / e2 — fused into its epilogue (dgradT.cuh); that gate gradient lands in dz[buf^1].
@@ -969,17 +747,17 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
   f.dc = cn.dc;
   f.dz_out = ctx.dzb[buf ^ 1];
   f.bias_partial = cn.bpart;
+  f.dz_absmax = ctx.amax + 1;
   f.HP = HP;
-  f.pf_dist = env_int("CLSTM_FUSE_PF", 1);
-  return launch_dgradT_fused<E>(ctx.dev, ctx.m_dz128b[buf], cs.m_wdT, cs.m_dhT, ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0},
+  f.pf_dist = ctx.knobs.fuse_pf;
+  return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.m_dhT, ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0},
                                 ctx.geo, ctx.geo.B, f, st);
 }
 
 // Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
 inline bool fuse_supported(const Ctx& ctx) {
-  const bool halo_dgrad = ctx.rows_ok && env_int("CLSTM_DGRADT_HALO", 0);
-  return !halo_dgrad && ctx.HP == 64 && ctx.geo.BW >= 16 && ctx.geo.npix() * 4 * ctx.HP < (1ull << 32) &&
-         env_int("CLSTM_DGRADT", 1) && env_int("CLSTM_FUSE_GATE", 1);
+  return ctx.HP == 64 && ctx.geo.BW >= 16 && ctx.geo.npix() * 4 * ctx.HP < (1ull << 32) && ctx.knobs.dgradT &&
+         ctx.knobs.fuse_gate;
 }
 
 template <typename E>
@@ -1004,11 +782,11 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
   p.accumulate = !first;
   // halo rows: both segments 3x3 convs over one 64-channel chunk, 64-pixel single-row K steps, groups of 6 taps
   if (!g.in_col && g.kh == 3 && g.kw == 3 && g.CIP == 64 && ctx.HP == 64 && geo.BW2 == 64 && geo.BH2 == 1 &&
-      cs.wg_group == 6 && cs.wg_total == 18 && in.map66 != nullptr && env_int("CLSTM_WG_HALO", 1)) {
+      cs.wg_group == 6 && cs.wg_total == 18 && in.map66 != nullptr && ctx.knobs.wg_halo) {
     p.halo = 1;
-    return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st, gate);
+    return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st, gate);
   }
-  return launch_wgrad<E>(ctx.dev, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st, gate);
+  return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st, gate);
 }
 
 template <typename E>
@@ -1094,7 +872,7 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   ctx.scale = cv.take<float>(64);
   ctx.amax = reinterpret_cast<unsigned int*>(cv.take<float>(64));
   p->xcol = cv.take<void>(static_cast<size_t>(c.t_in) * npix * p->KX * 2);
-  for (int k = 0; k < p->ncell; ++k) carve_cell(cv, p->cells[k], ctx);
+  for (int k = 0; k < p->ncell; ++k) carve_cell(cv, cv, p->cells[k], ctx);
   p->wh = cv.take<void>(static_cast<size_t>(p->NT) * 9 * HP * 2);
   p->bias_h = cv.take<float>(static_cast<size_t>(p->NT) * 4);
   p->wz = (c.out_channels <= 16) ? cv.take<void>(static_cast<size_t>(HP / 64) * kHrN * 64 * 2) : nullptr;
@@ -1118,40 +896,21 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   p->ws_bytes = align_up(cv.off, 1024);
 }
 
-// Full state stacks are PERMUTED (hslot / cslot above): consecutive time steps live
-// slot_stride slots apart (mod the slot count).  Measured on B200 (DESIGN.md §4 "slot placement"): a cell step
-// that reads h slot m while writing h slot m +- 1 (128 MB away) loses ~100 us to the write stream; 3 slots
-// apart costs ~15 us.
-inline int pick_stride(int slots, int want) {
-  if (slots <= 3 || want <= 1) return 1;
-  auto gcd = [](int a, int b) {
-    while (b) {
-      const int t = a % b;
-      a = b, b = t;
-    }
-    return a;
-  };
-  for (int k = want; k < slots; ++k)
-    if (gcd(k, slots) == 1) return k;
-  return 1;
-}
-
 // Input of cell k at its step t (conv_lstm.py:176-196).
 InputRef plan_input(clstm_plan* p, int k, int t) {
   InputRef in;
   const int B = p->cfg.batch;
   const int L = p->L;
   if (k == 0) {
-    in.map128 = &p->m_xcol128, in.map64 = &p->m_xcol64, in.maphalo = &p->m_xcol128, in.b_off = t * B;  // x[:, t] (:177)
+    in.map128 = &p->m_xcol128, in.map64 = &p->m_xcol64, in.b_off = t * B;  // x[:, t] (:177)
   } else if (k == L) {
     // decoder_1 input: encoder_vector (:185, :189) = last encoder h at t == 0, else last decoder h (:195)
     const CellState& src = (t == 0) ? p->cells[L - 1] : p->cells[p->ncell - 1];
     const int s = (t == 0) ? hslot(src, p->cfg.t_in) : hslot(src, t);
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.maphalo = &src.m_hhalo, in.b_off = s * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.b_off = s * B;
   } else {
     const CellState& src = p->cells[k - 1];  // the layer below, already stepped to t + 1 (:180, :192)
-    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.maphalo = &src.m_hhalo,
-    in.b_off = hslot(src, t + 1) * B;
+    in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.b_off = hslot(src, t + 1) * B;
   }
   return in;
 }
@@ -1225,8 +984,8 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
   // of y directly — the reference's stack / permute copies (:198-199) never exist.
   {
     const CellState& last = p->cells[p->ncell - 1];
-    const bool contiguous = (last.h_stride == 1 && last.h_rot == 0);  // slots 1..T_out adjacent in memory
-    const int launches = contiguous ? 1 : c.t_out;
+    const bool contiguous = true;  // slots 1..T_out of the last decoder's h stack are adjacent in memory
+    const int launches = 1;
     for (int t = 0; t < launches; ++t) {
       ConvGemmParams hp;
       memset(&hp, 0, sizeof(hp));
@@ -1251,16 +1010,10 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
         rp.bias = p->bias_h;
         rp.y = y;
         bool used = false;
-        RC_TRY((launch_head_rows<E>(ctx.dev, last.m_h128, p->m_wz, rp, geo, st, &used)));
+        RC_TRY((launch_head_rows<E>(ctx, last.m_h128, p->m_wz, rp, geo, st, &used)));
         if (used) continue;
       }
-      if (ctx.pair_ok && env_int("CLSTM_HALO2_HEAD", 0)) {
-        bool used = false;
-        RC_TRY((launch_halo2<E, EPI_HEAD>(ctx.dev, last.m_hhalo3, last.m_hhalo3, p->m_wh, p->m_wh, p->m_wh, p->m_wh, hp, geo,
-                                          images, st, &used)));
-        if (used) continue;
-      }
-      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx.dev, last.m_h128, last.m_h128, p->m_wh, hp, geo, images, st)));
+      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx, last.m_h128, last.m_h128, p->m_wh, hp, geo, images, st)));
     }
   }
   p->forward_done = true;
@@ -1278,7 +1031,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   const int L = p->L, ncell = p->ncell;
   // loss scale for the 16-bit gradient operands (device side, no sync) and the head bias gradient (sum of dlogit,
   // unscaled): one pass over dy and y
-  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 4, st));
+  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 16, st));  // [0] max |dlogit|, [1] max |S * dz| (float bits)
   {
     const size_t per_b = static_cast<size_t>(c.t_out) * c.height * c.width;
     dim3 grid(p->hb_chunks, c.batch * c.out_channels);
@@ -1304,7 +1057,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   // chain) and W = wgrad (tensor bound, off the chain: only the final reduction needs it).  W runs on a side
   // stream and is released when D has been issued, so W of step n executes concurrently with G of step n+1
   // (the gate-grad kernel is small enough to co-reside with a wgrad CTA on every SM) — two dz buffers alternate.
-  const bool overlap = env_int("CLSTM_OVERLAP", 0) != 0 && ctx.side != nullptr;
+  const bool overlap = ctx.knobs.overlap != 0 && ctx.side != nullptr;
   int nstep = 0;
   if (overlap) {
     CU_TRY(cudaEventRecord(ctx.ev_fork, st));
@@ -1353,7 +1106,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       hp.out0 = p->dstack, hp.out1 = p->dstack;
       hp.split_col = HP, hp.ld0 = HP, hp.ld1 = HP;
       hp.out_scale = 1.f;
-      RC_TRY((launch_convgemm<E, EPI_STORE>(ctx.dev, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st,
+      RC_TRY((launch_convgemm<E, EPI_STORE>(ctx, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st,
                                             &p->m_dstack16, &p->m_dstack16, &p->m_dstack16)));
     }
     {
@@ -1367,7 +1120,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       wp.splits = p->head_splits;
       wp.partial = p->hpart;
       wp.accumulate = (t != c.t_out - 1);
-      RC_TRY((launch_wgrad<E>(ctx.dev, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st)));
+      RC_TRY((launch_wgrad<E>(ctx, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st)));
     }
     return 0;
   };
@@ -1396,7 +1149,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
   const bool fuse = !overlap && L >= 2 && fuse_supported(ctx);
   // Experimental alternative (CLSTM_WG_GATE=1, off): the gate gradient of step n+1 rides along with WGRAD n instead
   // of the dgrad epilogue — 16 extra warps in the wgrad CTAs (wgrad.cuh), plain dgradT writes dx again.
-  const bool wg_gate = !overlap && HP == 64 && npix * 4 * HP < (1ull << 32) && env_int("CLSTM_WG_GATE", 0);
+  const bool wg_gate = !overlap && HP == 64 && npix * 4 * HP < (1ull << 32) && ctx.knobs.wg_gate;
   int bias_rows = kGateGradBlocks;
   if (wg_gate) {
     bias_rows = kBiasRowsMax;
@@ -1434,6 +1187,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
         gw.dc = cn.dc;
         gw.dz_out = ctx.dzb[b ^ 1];
         gw.bias_partial = cn.bpart;
+        gw.dz_absmax = ctx.amax + 1;
         gw.npix = static_cast<unsigned>(npix);
         RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b, &gw));
         gate_done = true;
@@ -1530,26 +1284,29 @@ struct clstm_cell_plan {
   Ctx ctx;
   CellState cs;
   int cin = 0, hid = 0;
-  size_t ws_bytes = 0;
+  size_t saved_bytes = 0, scratch_bytes = 0;
   bool bound = false, forward_done = false;
   void* xin = nullptr;  // E [npix][CIP]
-  CUtensorMap m_x128, m_x64, m_xhalo;
+  CUtensorMap m_x128, m_x64;
 };
 
 namespace {
 
-void carve_cell_plan(clstm_cell_plan* p, uint8_t* base) {
-  Carver cv;
-  cv.base = base;
+// saved region: packed x, packed weights, h / c (both steps), gates — everything clstm_cell_backward reads that the
+// forward wrote; scratch region: loss scale, dz, dh / dx / dc, split partials.
+void carve_cell_plan(clstm_cell_plan* p, uint8_t* saved, uint8_t* scratch) {
+  Carver sv, sc;
+  sv.base = saved, sc.base = scratch;
   Ctx& ctx = p->ctx;
   const size_t npix = ctx.geo.npix();
-  ctx.scale = cv.take<float>(64);
-  ctx.amax = reinterpret_cast<unsigned int*>(cv.take<float>(64));
-  p->xin = cv.take<void>(npix * p->cs.g.CIP * 2);
-  carve_cell(cv, p->cs, ctx);
-  ctx.dz = cv.take<void>(npix * 4 * ctx.HP * 2);
+  ctx.scale = sc.take<float>(64);
+  ctx.amax = reinterpret_cast<unsigned int*>(sc.take<float>(64));
+  p->xin = sv.take<void>(npix * p->cs.g.CIP * 2);
+  carve_cell(sv, sc, p->cs, ctx);
+  ctx.dz = sc.take<void>(npix * 4 * ctx.HP * 2);
   ctx.dzb[0] = ctx.dzb[1] = ctx.dz;
-  p->ws_bytes = align_up(cv.off, 1024);
+  p->saved_bytes = align_up(sv.off, 1024);
+  p->scratch_bytes = align_up(sc.off, 1024);
 }
 
 template <typename E>
@@ -1571,7 +1328,7 @@ int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, con
   pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(c_cur, cs.c, geo.B, p->hid, geo.H, geo.W, HP, nullptr);
   RC_TRY(after_launch("pack_nhwc_f32_kernel"));
   InputRef in;
-  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.maphalo = &p->m_xhalo, in.b_off = 0;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
   RC_TRY(cell_forward_step<E>(ctx, cs, in, 0, 1, cs.c, cs.c + npix * HP, cs.gates, st, 0, 1, 0));
   if (h_next) {
     unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(static_cast<const E*>(cs.h) + npix * HP, h_next, geo.B, p->hid,
@@ -1598,7 +1355,7 @@ int cellplan_backward(clstm_cell_plan* p, const float* dh_next, const float* dc_
   (void)weight;  // the packed copies made by the preceding forward are used
   // Loss scale for the 16-bit dz operand: S = 2^k with S * max(|dh_next|, |dc_next|) ~ 2^10 (device side).
   const size_t nstate = static_cast<size_t>(geo.B) * p->hid * geo.H * geo.W;
-  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 4, st));
+  CU_TRY(cudaMemsetAsync(ctx.amax, 0, 16, st));
   if (dh_next) {
     abs_amax_kernel<<<kPackBlocks, 256, 0, st>>>(dh_next, nstate, ctx.amax);
     RC_TRY(after_launch("abs_amax_kernel"));
@@ -1624,7 +1381,7 @@ int cellplan_backward(clstm_cell_plan* p, const float* dh_next, const float* dc_
   }
   cs.bwd_started = false;
   InputRef in;
-  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.maphalo = &p->m_xhalo, in.b_off = 0;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
   RC_TRY(cell_backward_step<E>(ctx, cs, in, 0, cs.gates, cs.c, cs.c + npix * HP, dh_src, nullptr, nullptr, st));
   RC_TRY(cell_finalize(ctx, cs, dweight, dbias, 0, st));
   if (dx) {
@@ -1751,7 +1508,7 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
   DeviceInfo dev;
   if (get_device(&dev) == 0) ctx.dev = dev;
   ctx.geo = make_geo(cfg->batch, cfg->height, cfg->width);
-  ctx.pair_ok = (ctx.geo.BW == 128 && ctx.geo.BH == 1);
+  ctx.knobs.read();
   ctx.dtype = cfg->dtype;
   ctx.HP = pad_hidden(cfg->hidden);
   ctx.training = cfg->training;
@@ -1770,15 +1527,12 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
     const bool full = cfg->training || k == p->ncell - 1;  // the head reads every last-decoder h
     cs.slots_h = full ? T + 1 : 2;
     cs.slots_c = cfg->training ? T + 1 : 2;
-    cs.h_stride = pick_stride(cs.slots_h, env_int("CLSTM_SLOT_STRIDE", 1));
-    cs.h_rot = cs.slots_h > 3 ? (env_int("CLSTM_SLOT_ROT", 0) * k) % cs.slots_h : 0;
-    cs.c_stride = pick_stride(cs.slots_c, env_int("CLSTM_CSLOT_STRIDE", 1));
   }
   int nt = 256;
   while (ctx.HP % nt) nt -= 64;
   p->n_tile_hd = nt;
   const long long p_tiles = static_cast<long long>(ctx.geo.B) * ctx.geo.tiles_w2 * ctx.geo.tiles_h2;
-  wgrad_shape(ctx.dev, ctx.HP / 64, p->KG / 128, p_tiles, &p->head_group, &p->head_splits);
+  wgrad_shape(ctx.dev, ctx.knobs.wg_group, ctx.HP / 64, p->KG / 128, p_tiles, &p->head_group, &p->head_splits);
   carve_plan(p, nullptr);
   *out = p;
   return 0;
@@ -1829,7 +1583,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
   const long long ximgs = static_cast<long long>(c.t_in) * c.batch;
   RC_TRY(make_map_act(&p->m_xcol128, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW, g.BH));
   RC_TRY(make_map_act(&p->m_xcol64, ctx.dtype, p->xcol, p->KX, g.W, g.H, ximgs, g.BW2, g.BH2));
-  RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT / weight_boxes(p->NT)));
+  RC_TRY(make_map_w(&p->m_wh, ctx.dtype, p->wh, 9 * ctx.HP, p->NT, p->NT));
   if (p->wz) RC_TRY(make_map_w(&p->m_wz, ctx.dtype, p->wz, 64, (ctx.HP / 64) * kHrN, kHrN));
   if (c.training) {
     RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
@@ -1837,11 +1591,6 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     for (int i = 0; i < 2; ++i) {
       RC_TRY(make_map_act(&ctx.m_dz128b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
       RC_TRY(make_map_act(&ctx.m_dz64b[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, g.BW2, g.BH2));
-      if (g.W > 128) {
-        RC_TRY(make_map_act(&ctx.m_dzrow256[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 256, 1));
-        RC_TRY(make_map_act(&ctx.m_dzrow8[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 8, 1));
-        ctx.rows_ok = true;
-      }
     }
     if (!ctx.side) {
       CU_TRY(cudaStreamCreateWithFlags(&ctx.side, cudaStreamNonBlocking));
@@ -1851,14 +1600,9 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
       }
       CU_TRY(cudaEventCreateWithFlags(&ctx.ev_fork, cudaEventDisableTiming));
     }
-    if (ctx.pair_ok) {
-      RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
-      for (int i = 0; i < 2; ++i)
-        RC_TRY(make_map_act(&ctx.m_dzhalob[i], ctx.dtype, ctx.dzb[i], 4 * ctx.HP, g.W, g.H, c.batch, 128 + c.kernel_w - 1, 1));
-    }
     RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
-    RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd / weight_boxes(p->n_tile_hd)));
+    RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
     RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
   p->bound = true;
@@ -1909,6 +1653,13 @@ int clstm_rollout_backward(clstm_plan_t* p, const float* dy, const float* y, flo
 #define CALL_(E) plan_backward<E>(p, dy, y, grads, accumulate, st)
   return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
+}
+
+int clstm_plan_grad_status(clstm_plan_t* p, float* out4, void* stream) {
+  if (!p || !out4) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound || !p->cfg.training) return fail(CLSTM_ESTATE, "grad_status needs a bound training plan");
+  grad_status_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(p->ctx.scale, p->ctx.amax, out4);
+  return after_launch("grad_status_kernel");
 }
 
 int clstm_plan_read_state(clstm_plan_t* p, int cell, int step, float* h_out, float* c_out, void* stream) {
@@ -2007,7 +1758,7 @@ int clstm_cell_plan_create(int batch, int height, int width, int in_channels, in
   DeviceInfo dev;
   if (get_device(&dev) == 0) ctx.dev = dev;
   ctx.geo = make_geo(batch, height, width);
-  ctx.pair_ok = (ctx.geo.BW == 128 && ctx.geo.BH == 1);
+  ctx.knobs.read();
   ctx.dtype = dtype;
   ctx.HP = pad_hidden(hidden);
   ctx.training = 1;
@@ -2015,7 +1766,7 @@ int clstm_cell_plan_create(int batch, int height, int width, int in_channels, in
   p->cin = in_channels, p->hid = hidden;
   init_cell(&p->cs, ctx, in_channels, hidden, kernel_h, kernel_w, 0, 1, 1);
   p->cs.slots_h = 2, p->cs.slots_c = 2;
-  carve_cell_plan(p, nullptr);
+  carve_cell_plan(p, nullptr, nullptr);
   *out = p;
   return 0;
 }
@@ -2025,20 +1776,38 @@ int clstm_cell_plan_destroy(clstm_cell_plan_t* plan) {
   return 0;
 }
 
-size_t clstm_cell_plan_workspace_bytes(const clstm_cell_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+size_t clstm_cell_plan_workspace_bytes(const clstm_cell_plan_t* plan) {
+  return plan ? plan->saved_bytes + plan->scratch_bytes : 0;
+}
+size_t clstm_cell_plan_saved_bytes(const clstm_cell_plan_t* plan) { return plan ? plan->saved_bytes : 0; }
+size_t clstm_cell_plan_scratch_bytes(const clstm_cell_plan_t* plan) { return plan ? plan->scratch_bytes : 0; }
 
 int clstm_cell_plan_bind(clstm_cell_plan_t* p, void* workspace, size_t bytes, void* stream) {
   if (!p || !workspace) return fail(CLSTM_EINVAL, "null argument");
-  if (bytes < p->ws_bytes) return fail(CLSTM_EINVAL, "workspace too small: %zu < %zu", bytes, p->ws_bytes);
-  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(CLSTM_EINVAL, "workspace must be 1024-byte aligned");
+  if (bytes < p->saved_bytes + p->scratch_bytes)
+    return fail(CLSTM_EINVAL, "workspace too small: %zu < %zu", bytes, p->saved_bytes + p->scratch_bytes);
+  return clstm_cell_plan_bind_split(p, workspace, p->saved_bytes, static_cast<uint8_t*>(workspace) + p->saved_bytes,
+                                    bytes - p->saved_bytes, stream);
+}
+
+int clstm_cell_plan_bind_split(clstm_cell_plan_t* p, void* saved, size_t saved_bytes, void* scratch,
+                               size_t scratch_bytes, void* stream) {
+  if (!p || !saved || !scratch) return fail(CLSTM_EINVAL, "null argument");
+  if (saved_bytes < p->saved_bytes) return fail(CLSTM_EINVAL, "saved region too small: %zu < %zu", saved_bytes, p->saved_bytes);
+  if (scratch_bytes < p->scratch_bytes)
+    return fail(CLSTM_EINVAL, "scratch region too small: %zu < %zu", scratch_bytes, p->scratch_bytes);
+  if (reinterpret_cast<uintptr_t>(saved) % 1024 || reinterpret_cast<uintptr_t>(scratch) % 1024)
+    return fail(CLSTM_EINVAL, "workspace regions must be 1024-byte aligned");
   (void)stream;
   Ctx& ctx = p->ctx;
-  DeviceInfo dev;
-  RC_TRY(get_device(&dev));
-  if (ctx.dev.sms != 0 && ctx.dev.sms != dev.sms) return fail(CLSTM_ESTATE, "plan created for a different device");
-  if (ctx.dev.sms == 0 && dev.sms != 148) return fail(CLSTM_ESTATE, "plan created without a device assumed 148 SMs");
-  ctx.dev = dev;
-  carve_cell_plan(p, static_cast<uint8_t*>(workspace));
+  if (ctx.dev.ordinal < 0 || !p->bound) {  // first bind: pin the device (later re-binds are host-only pointer updates)
+    DeviceInfo dev;
+    RC_TRY(get_device(&dev));
+    if (ctx.dev.sms != 0 && ctx.dev.sms != dev.sms) return fail(CLSTM_ESTATE, "plan created for a different device");
+    if (ctx.dev.sms == 0 && dev.sms != 148) return fail(CLSTM_ESTATE, "plan created without a device assumed 148 SMs");
+    ctx.dev = dev;
+  }
+  carve_cell_plan(p, static_cast<uint8_t*>(saved), static_cast<uint8_t*>(scratch));
   const Geo& g = ctx.geo;
   RC_TRY(map_cell(p->cs, ctx));
   RC_TRY(make_map_act(&p->m_x128, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
@@ -2046,13 +1815,7 @@ int clstm_cell_plan_bind(clstm_cell_plan_t* p, void* workspace, size_t bytes, vo
   RC_TRY(make_map_act(&ctx.m_dz128, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
   RC_TRY(make_map_act(&ctx.m_dz64, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, g.BW2, g.BH2));
   for (int i = 0; i < 2; ++i) ctx.m_dz128b[i] = ctx.m_dz128, ctx.m_dz64b[i] = ctx.m_dz64;
-  if (ctx.pair_ok) {
-    RC_TRY(make_map_act(&ctx.m_dzhalo, ctx.dtype, ctx.dz, 4 * ctx.HP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
-    ctx.m_dzhalob[0] = ctx.m_dzhalob[1] = ctx.m_dzhalo;
-    RC_TRY(make_map_act(&p->m_xhalo, ctx.dtype, p->xin, p->cs.g.CIP, g.W, g.H, g.B, 128 + p->cs.g.kw - 1, 1));
-  }
   p->bound = true;
-  p->forward_done = false;
   return 0;
 }
 
@@ -2069,7 +1832,8 @@ int clstm_cell_forward(clstm_cell_plan_t* p, const float* x, const float* h_cur,
 int clstm_cell_backward(clstm_cell_plan_t* p, const float* dh_next, const float* dc_next, const float* weight,
                         float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, void* stream) {
   if (!p) return fail(CLSTM_EINVAL, "null argument");
-  if (!p->forward_done) return fail(CLSTM_ESTATE, "clstm_cell_backward before clstm_cell_forward");
+  if (!p->bound) return fail(CLSTM_ESTATE, "clstm_cell_backward before clstm_cell_plan_bind");
+  if (!p->forward_done) return fail(CLSTM_ESTATE, "clstm_cell_backward before any clstm_cell_forward on this plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL_(E) cellplan_backward<E>(p, dh_next, dc_next, weight, dx, dh_cur, dc_cur, dweight, dbias, st)
   return DISPATCH_E(p->ctx.dtype, CALL_);
@@ -2094,18 +1858,6 @@ int clstm_mse_loss_grad(const float* y, const float* target, int batch, int chan
   mse_finalize_kernel<<<1, 1024, 0, st>>>(partial, out, batch, channels, t_out, static_cast<float>(1.0 / n),
                                           static_cast<float>(static_cast<double>(t_out) / n));
   return after_launch("mse_finalize_kernel");
-}
-
-// ---------------------------------------------------------------------------- bring-up experiments
-int clstm_selftest_shifted_desc(float* out_max_abs_err, int n_variants, int n_shifts, void* stream) {
-  if (!out_max_abs_err || n_variants < 1 || n_shifts < 1) return fail(CLSTM_EINVAL, "bad argument");
-  DeviceInfo dev;
-  RC_TRY(get_device(&dev));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return run_shifted_desc_selftest(out_max_abs_err, n_variants, n_shifts, st, &g_launches) == 0
-             ? 0
-             : fail(CLSTM_ECUDA, "shifted-descriptor self test failed to launch: %s",
-                    cudaGetErrorString(cudaGetLastError()));
 }
 
 }  // extern "C"

@@ -60,11 +60,7 @@ struct ConvGemmParams {
   int nseg;
   ConvSeg seg[2];
   int stages;
-  int hint_store, hint_w, hint_a;  // L2 cache hints: 0 none, 1 evict_first, 2 evict_last (stores / weights / A tiles)
-  int dbg_no_tma;   // experiment: after the first ring fill reuse shared memory (no TMA loads) -> pure MMA rate
-  int prod_serial;  // experiment: 1 = lane 0 issues every box of a stage itself
   int rotate;       // 1: tile t starts its K loop at k-block t % kblocks (needs kblocks <= kKtabMax), see producer
-  int b_boxes;  // the weight tile of a stage is loaded as b_boxes TMA boxes of n_tile / b_boxes rows (parallel issue)
   // ---- EPI_LSTM (n_tile == 256: gate-interleaved [i|f|o|g] x 64 hidden channels per N tile)
   const float* bias;  // [n_tiles * n_tile] in packed row order (all epilogues)
   const float* c_prev;  // fp32 [pixel][ldc] or nullptr (== zeros)
@@ -75,10 +71,6 @@ struct ConvGemmParams {
   // staged epilogue (TMA stores / c_prev TMA load): image offsets into the epilogue tensor maps
   int staged;           // 1: outputs go through shared memory + TMA (tmX0..tmX2), 0: direct per-thread stores
   int cprev_boff, cnext_boff, hnext_boff, gates_boff;
-  int lsu_mask;         // staged outputs written by cooperative st.global instead of TMA: bit 0 c, 1 h, 2 gates
-  int skip_mask;        // experiment: bit 0 skip c store, bit 1 skip h store, bit 2 skip gate stores
-  int act_mode;         // 0: one reciprocal per activation; 1: tanh.approx (experiment); 2: no MUFU (experiment);
-                        // 3: shared reciprocals (default)
   // ---- EPI_STORE
   float* out0;
   float* out1;
@@ -112,7 +104,7 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
       if (valid) {
         const size_t off = pix * p.ldc + nt * 64 + j0;
         float cp[16];
-        if (p.c_prev != nullptr && p.act_mode != 4) {
+        if (p.c_prev != nullptr) {
           const float4* src = reinterpret_cast<const float4*>(p.c_prev + off);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -124,58 +116,19 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
           for (int e = 0; e < 16; ++e) cp[e] = 0.f;
         }
         float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
-        if (p.act_mode == 3) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
-                                  __uint_as_float(vo[e]) + bs[128 + j0 + e],
-                                  __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
-            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-          }
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            float ta, tb;
-            tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
-            hn[e] = go[e] * ta;
-            hn[e + 1] = go[e + 1] * tb;
-          }
-        } else if (p.act_mode == 1) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            gi[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vi[e]) + bs[0 + j0 + e])), 0.5f);
-            gf[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vf[e]) + bs[64 + j0 + e])), 0.5f);
-            go[e] = fmaf(0.5f, tanh_mufu(0.5f * (__uint_as_float(vo[e]) + bs[128 + j0 + e])), 0.5f);
-            gg[e] = tanh_mufu(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-            hn[e] = go[e] * tanh_mufu(cn[e]);
-          }
-        } else if (p.act_mode == 2) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            gi[e] = __uint_as_float(vi[e]) + bs[0 + j0 + e];
-            gf[e] = __uint_as_float(vf[e]) + bs[64 + j0 + e];
-            go[e] = __uint_as_float(vo[e]) + bs[128 + j0 + e];
-            gg[e] = __uint_as_float(vg[e]) + bs[192 + j0 + e];
-            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-            hn[e] = go[e] * cn[e];
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
-            gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
-            go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
-            gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-            cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-            hn[e] = go[e] * fast_tanh(cn[e]);
-          }
+        for (int e = 0; e < 16; ++e) {
+          lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
+                                __uint_as_float(vo[e]) + bs[128 + j0 + e],
+                                __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+          cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
         }
-        if (p.act_mode == 4) {  // experiment: no epilogue stores (one predicated-off store keeps the math alive)
-          float acc_x = 0.f;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) acc_x += cn[e] + hn[e] + gi[e] + gf[e] + go[e] + gg[e];
-          if (acc_x == 1.2345e30f) p.c_next[off] = acc_x;
-          continue;
+        for (int e = 0; e < 16; e += 2) {
+          float ta, tb;
+          tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
+          hn[e] = go[e] * ta;
+          hn[e + 1] = go[e + 1] * tb;
         }
         float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
 #pragma unroll
@@ -303,7 +256,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // One lane per box: lane 0 loads the A tile, lanes 1..b_boxes one slice of the weight tile each.  A single
+    // One lane per box: lane 0 loads the A tile, lane 1 the weight tile.  A single
     // thread issuing every cp.async.bulk.tensor of a stage serialises on the issue latency (measured: the wgrad
     // kernel went from 555 to 1250 TFLOP/s when its 8 boxes per stage were spread over 8 lanes).
     if (p.rotate) {
@@ -341,10 +294,10 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           }
         }
       }
-    } else if (lane <= (p.prod_serial ? 0 : p.b_boxes)) {
+    } else if (lane < 2) {
+      // plain K order (more k-blocks than the rotation table holds, or CLSTM_ROTATE=0)
       int stage = 0;
       uint32_t phase = 0;
-      const int b_rows = p.n_tile / p.b_boxes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int tw = mt % p.tiles_w;
@@ -360,28 +313,12 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int ch = 0; ch < sg.chunks; ++ch, ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* a_dst = smem + stage * stage_bytes;
-                if (p.dbg_no_tma && (tile != static_cast<int>(blockIdx.x) || kb >= p.stages)) {
-                  if (lane == 0) mbar_arrive(&full_bar[stage]);
-                } else if (lane == 0) {
+                if (lane == 0) {
                   mbar_expect_tx(&full_bar[stage], stage_bytes);
-                  if (p.hint_a)
-                    tma_load_4d_hint(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
-                                     h0 + dy - sg.kh / 2, b + sg.b_off, p.hint_a == 1 ? kEvictFirst : kEvictLast);
-                  else
-                    tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2,
-                                h0 + dy - sg.kh / 2, b + sg.b_off);
-                  if (p.prod_serial)
-                    for (int part = 0; part < p.b_boxes; ++part)
-                      tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
-                                  nt * p.n_tile + part * b_rows);
+                  tma_load_4d(a_dst, tmA, &full_bar[stage], ch * kBlockK, w0 + dx - sg.kw / 2, h0 + dy - sg.kh / 2,
+                              b + sg.b_off);
                 } else {
-                  const int part = lane - 1;
-                  if (p.hint_w)
-                    tma_load_2d_hint(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
-                                     nt * p.n_tile + part * b_rows, p.hint_w == 1 ? kEvictFirst : kEvictLast);
-                  else
-                    tma_load_2d(a_dst + kABytes + part * b_rows * 128, &tmB, &full_bar[stage], kb * kBlockK,
-                                nt * p.n_tile + part * b_rows);
+                  tma_load_2d(a_dst + kABytes, &tmB, &full_bar[stage], kb * kBlockK, nt * p.n_tile);
                 }
                 if (++stage == p.stages) {
                   stage = 0;
@@ -455,7 +392,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         b = mt / (p.tiles_w * p.tiles_h);
       };
       if constexpr (EPI == EPI_LSTM) {
-        const bool has_cprev = p.cprev_boff >= 0 && p.act_mode != 6;
+        const bool has_cprev = p.cprev_boff >= 0;
         uint32_t cp_phase = 0;
         if (issuer && has_cprev && static_cast<int>(blockIdx.x) < total_tiles) {
           int nt, w0, h0, b;
@@ -507,31 +444,19 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
             tmem_ld_wait();
             float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
-            if (p.act_mode == 0) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                gi[e] = fast_sigmoid(__uint_as_float(vi[e]) + bs[0 + j0 + e]);
-                gf[e] = fast_sigmoid(__uint_as_float(vf[e]) + bs[64 + j0 + e]);
-                go[e] = fast_sigmoid(__uint_as_float(vo[e]) + bs[128 + j0 + e]);
-                gg[e] = fast_tanh(__uint_as_float(vg[e]) + bs[192 + j0 + e]);
-                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-                hn[e] = go[e] * fast_tanh(cn[e]);
-              }
-            } else {
+            for (int e = 0; e < 16; ++e) {
+              lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
+                                    __uint_as_float(vo[e]) + bs[128 + j0 + e],
+                                    __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+              cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+            }
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
-                                      __uint_as_float(vo[e]) + bs[128 + j0 + e],
-                                      __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
-                cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
-              }
-#pragma unroll
-              for (int e = 0; e < 16; e += 2) {
-                float ta, tb;
-                tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
-                hn[e] = go[e] * ta;
-                hn[e + 1] = go[e + 1] * tb;
-              }
+            for (int e = 0; e < 16; e += 2) {
+              float ta, tb;
+              tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
+              hn[e] = go[e] * ta;
+              hn[e + 1] = go[e + 1] * tb;
             }
             if (g2 == 1) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
               tcgen05_fence_before();
@@ -560,63 +485,16 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
-            if (p.lsu_mask) {
-              // Cooperative coalesced stores: the half's 128 threads sweep the staged [128 px x 16 ch] group in
-              // 16-byte chunks, consecutive threads -> consecutive chunks of a pixel, then the next pixel.
-              // (TMA stores of these 32/64-byte rows were request-rate bound: DESIGN.md §4.)
-              const int chan = nt * 64 + j0;
-              const int lbw = 31 - __clz(p.BW);
-              auto pixel_of = [&](int px, size_t& gp) {
-                const int hy = h0 + (px >> lbw), wx = w0 + (px & (p.BW - 1));
-                gp = (static_cast<size_t>(b) * p.H + hy) * p.W + wx;
-                return hy < p.H && wx < p.W;
-              };
-              if (p.act_mode < 5) {
-                if (p.lsu_mask & 1) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {  // c: 4 chunks per pixel
-                  const uint32_t idx = it * 128 + r, px = idx >> 2, ch = idx & 3;
-                  const float4 v = *reinterpret_cast<const float4*>(stg + kStgC + px * 64 + ((ch ^ ((px >> 1) & 3)) << 4));
-                  size_t gp;
-                  if (pixel_of(px, gp)) *reinterpret_cast<float4*>(p.c_next + gp * p.ldc + chan + ch * 4) = v;
-                }
-                }
-                if (p.lsu_mask & 2) {
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {  // h: 2 chunks per pixel
-                  const uint32_t idx = it * 128 + r, px = idx >> 1, ch = idx & 1;
-                  const uint4 v = *reinterpret_cast<const uint4*>(stg + kStgH + px * 32 + ((ch ^ ((px >> 2) & 1)) << 4));
-                  size_t gp;
-                  if (pixel_of(px, gp))
-                    *reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.h_next) + gp * p.ldc + chan + ch * 8) = v;
-                }
-                }
-                if (p.gates != nullptr && (p.lsu_mask & 4)) {
-#pragma unroll
-                  for (int it = 0; it < 8; ++it) {  // gates: 4 gates x 2 chunks per pixel
-                    const uint32_t idx = it * 128 + r, gt = idx >> 8, px = (idx & 255) >> 1, ch = idx & 1;
-                    const uint4 v = *reinterpret_cast<const uint4*>(stg + kStgG + gt * 4096 + px * 32 +
-                                                                    ((ch ^ ((px >> 2) & 1)) << 4));
-                    size_t gp;
-                    if (pixel_of(px, gp))
-                      *reinterpret_cast<uint4*>(reinterpret_cast<E*>(p.gates) + gp * (4 * static_cast<size_t>(p.ldc)) +
-                                                gt * p.ldc + chan + ch * 8) = v;
-                  }
-                }
-              }
-            }
-            if (q == 0 && lane < 6 && p.act_mode < 5) {
+            if (q == 0 && lane < 6) {
               // one lane per output box (c, h, 4 gates): parallel TMA issue
               const int chan = nt * 64 + j0;
-              const int skip = p.skip_mask | p.lsu_mask;
-              const uint64_t pol = p.hint_store == 1 ? kEvictFirst : (p.hint_store == 2 ? kEvictLast : kEvictNormal);
               if (lane == 0) {
-                if (!(skip & 1)) tma_store_4d_hint(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff, pol);
+                tma_store_4d(&tmX0, stg + kStgC, chan, w0, h0, b + p.cnext_boff);
               } else if (lane == 1) {
-                if (!(skip & 2)) tma_store_4d_hint(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff, pol);
-              } else if (p.gates_boff >= 0 && !(skip & 4)) {
+                tma_store_4d(&tmX1, stg + kStgH, chan, w0, h0, b + p.hnext_boff);
+              } else if (p.gates_boff >= 0) {
                 const int gt = lane - 2;
-                tma_store_4d_hint(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff, pol);
+                tma_store_4d(&tmX2, stg + kStgG + gt * 4096, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
               }
               tma_store_commit();
             }
@@ -651,7 +529,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                               __uint_as_float(v[4 * j + 2]) * p.out_scale, __uint_as_float(v[4 * j + 3]) * p.out_scale);
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 128);
-            if (issuer && !(p.skip_mask & 1)) {
+            if (issuer) {
               const int col = nt * p.n_tile + g * 16;
               if (col < p.split_col)
                 tma_store_4d(&tmX0, stg, col, w0, h0, b);

@@ -16,6 +16,7 @@
 // quadrant split the 256 pixel columns).
 #pragma once
 #include "convgemm.cuh"
+#include "pointwise.cuh"
 
 namespace clstm {
 
@@ -247,6 +248,7 @@ struct GateFuse {
   float* dc;             // in/out
   void* dz_out;          // E [pix][4*HP]
   float* bias_partial;   // [gridDim.x][4*HP], accumulated
+  unsigned int* dz_absmax;  // range statistics of the 16-bit dz this pass writes (float bits, see fold_absmax)
   int HP;
 };
 
@@ -393,6 +395,7 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+    uint32_t zmax = 0;
 
     struct Raw {
       uint2 g[4];
@@ -457,36 +460,13 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
       if (s0_c) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
       if (s1_c) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
       if (s2_c) dhv[0] += r.s2.x, dhv[1] += r.s2.y, dhv[2] += r.s2.z, dhv[3] += r.s2.w;
-      float gv[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float2 p0 = Elem<E>::unpack2(r.g[a].x), p1 = Elem<E>::unpack2(r.g[a].y);
-        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
-      }
-      const float cp[4] = {r.cp.x, r.cp.y, r.cp.z, r.cp.w};
-      const float cn[4] = {r.cn.x, r.cn.y, r.cn.z, r.cn.w};
-      const float dcv[4] = {r.dc.x, r.dc.y, r.dc.z, r.dc.w};
-      float dzv[4][4], dcn[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
-        const float tc = fast_tanh(cn[e]);
-        const float d_o = dhv[e] * tc;
-        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
-        dzv[0][e] = dct * gg * gi * (1.f - gi);
-        dzv[1][e] = dct * cp[e] * gf * (1.f - gf);
-        dzv[2][e] = d_o * go * (1.f - go);
-        dzv[3][e] = dct * gi * (1.f - gg * gg);
-        dcn[e] = dct * gf;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
-      }
+      float4 dcn;
+      uint2 dzp[4];
+      gate_grad_item4<E>(r.g, r.cp, r.cn, r.dc, dhv, bsum, zmax, dcn, dzp);
       const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;
-      *reinterpret_cast<float4*>(dc_c + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+      *reinterpret_cast<float4*>(dc_c + o1) = dcn;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
-            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+      for (int a = 0; a < 4; ++a) *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) = dzp[a];
     };
 
     // L2 prefetch of the lines the NEXT group will load (costs no registers: the memory system holds the requests).
@@ -573,6 +553,7 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
       if (acc == 0) acc_phase ^= 1;
     }
     if (q == 0 && lane == 1) tma_store_wait_all();
+    fold_absmax<E>(zmax, f.dz_absmax);
     // bias partial sums: reduce over the 16 threads (both halves) that share a channel chunk, one gate at a time
     const int te = threadIdx.x - 128;  // over the epilogue warps; te & 15 == chunk
     float* red = reinterpret_cast<float*>(smem_stg);
@@ -590,220 +571,6 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
         }
       }
     }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-}  // namespace clstm
-
-// ======================================================================================================
-// Halo-row variant of the transposed dgrad (3x3 filters, W > 128): a unit is 256 consecutive pixels of ONE image
-// row.  For each 64-channel chunk of dz the three image rows h-1, h, h+1 are loaded once as [258 px x 64 ch] rows
-// (a 256-pixel box plus an 8-pixel box) into a ring of row slots; tap (dy, dx) is the B descriptor of row dy
-// shifted by dx pixels (N = 256 rows are contiguous inside a row slot).  Pixel-operand traffic drops from
-// 9 x 32 KB to 3 x 33 KB per chunk; with the 16 KB weight tile per tap that is 27 KB instead of 48 KB per k-block.
-// ======================================================================================================
-namespace clstm {
-
-constexpr int kDtRowPx = 264;                       // row slot pitch in pixels (258 used)
-constexpr int kDtRowBytes = kDtRowPx * 128;         // 33792
-constexpr int kDtMaxRows = 6;
-
-struct DgradTHaloParams {
-  int B, H, W;
-  int segs_w;      // ceil(W / 256)
-  int chunks;      // dz chunks (4HP / 64)
-  int m_tiles;
-  int w_stages;    // weight ring
-  int rows;        // row ring
-  int split_col;
-};
-
-inline size_t dgradTh_smem_bytes(int w_stages, int rows) {
-  return 1024 + static_cast<size_t>(w_stages) * 16384 + static_cast<size_t>(rows) * kDtRowBytes + 2 * kDtStgHalf +
-         (2 * kMaxStages + 2 * kDtMaxRows + 4) * 8 + 16 + 64;
-}
-
-template <typename E>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-dgradT_halo_kernel(const __grid_constant__ CUtensorMap tmRow256, const __grid_constant__ CUtensorMap tmRow8,
-                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX0,
-                   const __grid_constant__ CUtensorMap tmX1, const DgradTHaloParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_w = smem;
-  uint8_t* smem_r = smem_w + p.w_stages * 16384;
-  uint8_t* smem_stg = smem_r + p.rows * kDtRowBytes;
-  uint8_t* tail = smem_stg + 2 * kDtStgHalf;
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* w_empty = w_full + kMaxStages;
-  uint64_t* r_full = w_empty + kMaxStages;
-  uint64_t* r_empty = r_full + kDtMaxRows;
-  uint64_t* tmem_full = r_empty + kDtMaxRows;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_units = p.B * p.H * p.segs_w * p.m_tiles;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmRow256);
-    tma_prefetch_desc(&tmRow8);
-    tma_prefetch_desc(&tmW);
-    for (int s = 0; s < p.w_stages; ++s) {
-      mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
-    }
-    for (int s = 0; s < p.rows; ++s) {
-      mbar_init(&r_full[s], 1);
-      mbar_init(&r_empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  auto decode = [&](int unit, int& mtile, int& w0, int& h, int& b) {
-    mtile = unit % p.m_tiles;
-    int rest = unit / p.m_tiles;
-    w0 = (rest % p.segs_w) * 256;
-    rest /= p.segs_w;
-    h = rest % p.H;
-    b = rest / p.H;
-  };
-
-  if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t idx = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int mtile = unit % p.m_tiles;
-        for (int ch = 0; ch < p.chunks; ++ch)
-          for (int tap = 0; tap < 9; ++tap, ++idx) {
-            const uint32_t stage = idx % p.w_stages;
-            mbar_wait(&w_empty[stage], ((idx / p.w_stages) & 1) ^ 1);
-            mbar_expect_tx(&w_full[stage], 16384);
-            tma_load_2d(smem_w + stage * 16384, &tmW, &w_full[stage], (tap * p.chunks + ch) * kBlockK, mtile * 128);
-          }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== halo-row producer: lane 0 the 256-pixel box, lane 1 the 8-pixel tail =====================
-    if (lane < 2) {
-      uint32_t idx = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        int mtile, w0, h, b;
-        decode(unit, mtile, w0, h, b);
-        for (int ch = 0; ch < p.chunks; ++ch)
-          for (int r = 0; r < 3; ++r, ++idx) {
-            const uint32_t slot = idx % p.rows;
-            mbar_wait(&r_empty[slot], ((idx / p.rows) & 1) ^ 1);
-            uint8_t* dst = smem_r + slot * kDtRowBytes;
-            if (lane == 0) {
-              mbar_expect_tx(&r_full[slot], 264 * 128);
-              tma_load_4d(dst, &tmRow256, &r_full[slot], ch * kBlockK, w0 - 1, h + r - 1, b);
-            } else {
-              tma_load_4d(dst + 256 * 128, &tmRow8, &r_full[slot], ch * kBlockK, w0 + 255, h + r - 1, b);
-            }
-          }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 256, 0, 0);
-      uint32_t w_idx = 0, r_idx = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + acc * 256;
-        uint32_t first = 1;
-        for (int ch = 0; ch < p.chunks; ++ch)
-          for (int dy = 0; dy < 3; ++dy, ++r_idx) {
-            const uint32_t slot = r_idx % p.rows;
-            mbar_wait(&r_full[slot], (r_idx / p.rows) & 1);
-            const uint32_t row = smem_u32(smem_r + slot * kDtRowBytes);
-            for (int dx = 0; dx < 3; ++dx, ++w_idx) {
-              const uint32_t stage = w_idx % p.w_stages;
-              mbar_wait(&w_full[stage], (w_idx / p.w_stages) & 1);
-              tcgen05_fence_after();
-              const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_w + stage * 16384), 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(row + dx * 128, 16, 1024);
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-              first = 0;
-              umma_commit(&w_empty[stage]);
-            }
-            umma_commit(&r_empty[slot]);
-          }
-        umma_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue (as dgradT_kernel; the unit's 256 pixels are one row segment) ==============
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int cl = q * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem_stg + half * kDtStgHalf);
-    const int bar_id = 1 + half;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      int mtile, w0, h, b;
-      decode(unit, mtile, w0, h, b);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + half * 128 + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        uint32_t v[16];
-        tmem_ld16(taddr + g * 16, v);
-        if (q == 0 && lane < 2) tma_store_wait_read();
-        named_bar_sync(bar_id, 128);
-        tmem_ld_wait();
-        if (g == 7) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        float* dst = stg + (cl >> 6) * (16 * 64) + (cl & 63);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j * 64] = __uint_as_float(v[j]);
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (q == 0 && lane < 2) {
-          const int wx = w0 + half * 128 + g * 16;
-          const int chan = mtile * 128 + lane * 64;
-          if (chan < p.split_col)
-            tma_store_4d(&tmX0, stg + lane * (16 * 64), chan, wx, h, b);
-          else
-            tma_store_4d(&tmX1, stg + lane * (16 * 64), chan - p.split_col, wx, h, b);
-          tma_store_commit();
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (q == 0 && lane < 2) tma_store_wait_all();
   }
 
   tcgen05_fence_before();

@@ -367,8 +367,9 @@ __global__ void __launch_bounds__(256)
 gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
                  const float* __restrict__ dh0, const float* __restrict__ dh1, const float* __restrict__ dh2,
                  float* __restrict__ dc, E* __restrict__ dz, float* __restrict__ bias_partial, int bias_accumulate,
-                 size_t npix, int HP) {
+                 size_t npix, int HP, unsigned int* __restrict__ dz_absmax) {
   extern __shared__ float red[];  // [256][9] padded
+  uint32_t zmax = 0;  // packed running max |dz| of this thread (range statistics, see fold_absmax)
   const int groups = HP / 8;
   const int grp = threadIdx.x % groups;
   const int plane = threadIdx.x / groups;
@@ -442,11 +443,13 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
     *reinterpret_cast<float4*>(dc + off + 4) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      *reinterpret_cast<uint4*>(dz + pix * 4 * HP + a * HP + grp * 8) =
-          make_uint4(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]),
-                     Elem<E>::pack2(dzv[a][4], dzv[a][5]), Elem<E>::pack2(dzv[a][6], dzv[a][7]));
+      const uint4 o = make_uint4(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]),
+                                 Elem<E>::pack2(dzv[a][4], dzv[a][5]), Elem<E>::pack2(dzv[a][6], dzv[a][7]));
+      zmax = Elem<E>::absmax2(Elem<E>::absmax2(Elem<E>::absmax2(Elem<E>::absmax2(zmax, o.x), o.y), o.z), o.w);
+      *reinterpret_cast<uint4*>(dz + pix * 4 * HP + a * HP + grp * 8) = o;
     }
   }
+  fold_absmax<E>(zmax, dz_absmax);
   // block reduction of the bias partial sums over the `ppb` pixel lanes (fixed order -> deterministic), one
   // gate at a time so the kernel needs only 256 x 9 floats of shared memory: it must be able to co-reside with
   // a weight-gradient CTA (198 KB of shared memory) on the same SM (DESIGN.md "backward overlap").
@@ -466,6 +469,56 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
     }
     __syncthreads();
   }
+}
+
+// The same math for one item of 1 pixel x 4 channels held in registers — the unit of work of the gate-gradient passes
+// that ride inside the GEMM kernels (dgradT_fused_kernel's epilogue, the worker warps of wgrad_kernel).
+//   g[a]: the four saved gates (packed 16-bit x4), cp / cn: c_prev / c_next, dcin: incoming dc, dhv: summed dh sources
+//   -> dz_out[a] packed 16-bit, dc_out = dct * f, bsum += dz (bias-gradient partial), zmax = running packed max |dz|
+template <typename E>
+__device__ __forceinline__ void gate_grad_item4(const uint2 (&g)[4], const float4& cp4, const float4& cn4,
+                                                const float4& dcin, const float (&dhv)[4], float (&bsum)[4][4],
+                                                uint32_t& zmax, float4& dc_out, uint2 (&dz_out)[4]) {
+  float gv[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float2 p0 = Elem<E>::unpack2(g[a].x), p1 = Elem<E>::unpack2(g[a].y);
+    gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+  }
+  const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+  const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+  const float dcv[4] = {dcin.x, dcin.y, dcin.z, dcin.w};
+  float dzv[4][4], dcn[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
+    const float tc = fast_tanh(cn[e]);
+    const float d_o = dhv[e] * tc;
+    const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
+    dzv[0][e] = dct * gg * gi * (1.f - gi);
+    dzv[1][e] = dct * cp[e] * gf * (1.f - gf);
+    dzv[2][e] = d_o * go * (1.f - go);
+    dzv[3][e] = dct * gi * (1.f - gg * gg);
+    dcn[e] = dct * gf;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
+  }
+  dc_out = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    dz_out[a] = make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+    zmax = Elem<E>::absmax2(Elem<E>::absmax2(zmax, dz_out[a].x), dz_out[a].y);
+  }
+}
+
+// out[0..3] = {S, 1/S, max |dlogit| of the head, max |S * dz| over every gate-gradient pass of the last backward}
+// (clstm_plan_grad_status; stats[0] / stats[1] hold float bits).
+__global__ void grad_status_kernel(const float* __restrict__ scale, const unsigned int* __restrict__ stats,
+                                   float* __restrict__ out) {
+  out[0] = scale[0];
+  out[1] = scale[1];
+  out[2] = __uint_as_float(stats[0]);
+  out[3] = __uint_as_float(stats[1]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -560,7 +613,9 @@ head_grad_stats_kernel(const float* __restrict__ dyv, const float* __restrict__ 
   if (threadIdx.x == 0) {
     partial[static_cast<size_t>(co) * (static_cast<size_t>(B) * chunks) + static_cast<size_t>(b) * chunks + chunk] = red_s[0];
     const float mm = red_m[0];
-    if (amax_bits != nullptr && mm > 0.f && mm < 3.0e38f) atomicMax(amax_bits, __float_as_uint(mm));
+    // a non-finite dy (NaN compares false everywhere) is recorded as +Inf so that the host can see it
+    const float ms = (red_s[0] - red_s[0] == 0.f && mm < 3.0e38f) ? mm : __uint_as_float(0x7F800000u);
+    if (amax_bits != nullptr && ms > 0.f) atomicMax(amax_bits, __float_as_uint(ms));
   }
 }
 
@@ -727,7 +782,7 @@ __global__ void choose_scale_kernel(const unsigned int* __restrict__ amax_bits, 
   if (!(fixed > 0.f)) {
     const float amax = __uint_as_float(*amax_bits);
     s = 1.f;
-    if (amax > 0.f) s = exp2f(floorf(log2f(target / amax)));
+    if (amax > 0.f && amax < 3.0e38f) s = exp2f(floorf(log2f(target / amax)));
     s = fminf(fmaxf(s, 1.0e-30f), 1.0e30f);
   }
   scale[0] = s;

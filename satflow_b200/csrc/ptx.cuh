@@ -283,6 +283,11 @@ struct Elem<__half> {
   }
   __device__ static __forceinline__ __half from_float(float a) { return __float2half_rn(a); }
   __device__ static __forceinline__ float to_float(__half a) { return __half2float(a); }
+  // running max of |v| over packed pairs, NaN-propagating (gradient range statistics: one HMNMX2 per pair)
+  __device__ static __forceinline__ uint32_t absmax2(uint32_t m, uint32_t v) {
+    __half2 r = __hmax2_nan(*reinterpret_cast<__half2*>(&m), __habs2(*reinterpret_cast<__half2*>(&v)));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <>
 struct Elem<__nv_bfloat16> {
@@ -296,7 +301,24 @@ struct Elem<__nv_bfloat16> {
   }
   __device__ static __forceinline__ __nv_bfloat16 from_float(float a) { return __float2bfloat16_rn(a); }
   __device__ static __forceinline__ float to_float(__nv_bfloat16 a) { return __bfloat162float(a); }
+  __device__ static __forceinline__ uint32_t absmax2(uint32_t m, uint32_t v) {
+    __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<__nv_bfloat162*>(&m), __habs2(*reinterpret_cast<__nv_bfloat162*>(&v)));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
+
+// Gradient range statistics: fold a thread's packed running |dz| maximum (Elem<E>::absmax2) into a device word holding
+// the float bits of the launch-wide maximum.  Non-negative floats order like unsigned integers; NaN and Inf are both
+// recorded as +Inf (0x7F800000), which is what "the 16-bit gradient operand overflowed" looks like to the host.
+template <typename E>
+__device__ __forceinline__ void fold_absmax(uint32_t packed, unsigned int* __restrict__ stat) {
+  const float2 f = Elem<E>::unpack2(packed);
+  float m = fmaxf(f.x, f.y);
+  if (!(f.x <= 3.0e38f) || !(f.y <= 3.0e38f)) m = __uint_as_float(0x7F800000u);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane_id() == 0 && m > 0.f) atomicMax(stat, __float_as_uint(m));
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));

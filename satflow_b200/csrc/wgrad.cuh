@@ -12,7 +12,7 @@
 // added into its private slice partial[split] -- deterministic, no atomics; a finalize kernel
 // reduces the splits (pointwise.cuh).
 #pragma once
-#include "ptx.cuh"
+#include "pointwise.cuh"
 
 namespace clstm {
 
@@ -45,7 +45,6 @@ struct WgradParams {
   float* partial;  // [splits][n_blocks*128][total_blocks*64] fp32
   int accumulate;  // 0: overwrite, 1: +=
   int halo;        // 1: 3x3 taps served from halo rows (see wgrad_kernel); requires chunks == 1, BW == 64, BH == 1
-  int dbg_no_tma;  // experiment: after the first ring fill, reuse shared memory (no TMA) -> pure MMA rate
 };
 
 // Gate-gradient work that can ride along with a wgrad launch (GATE = true): wgrad is tensor bound and leaves the CUDA
@@ -64,6 +63,7 @@ struct WgGateWork {
   float* dc;             // in/out
   void* dz_out;          // E [pix][4*HP]
   float* bias_partial;   // [gridDim.x * 16][4*HP]: one row per worker warp, accumulated
+  unsigned int* dz_absmax;  // range statistics of the dz written here (float bits, see fold_absmax)
   unsigned npix;         // HP == 64 and npix * 256 < 2^32 (checked on the host)
 };
 
@@ -135,6 +135,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+    uint32_t zmax = 0;
     struct Raw {
       uint2 g[4];
       float4 cp, cn, dc, s0, s1, s2;
@@ -160,36 +161,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (gw.src0) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
       if (gw.src1) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
       if (gw.src2) dhv[0] += r.s2.x, dhv[1] += r.s2.y, dhv[2] += r.s2.z, dhv[3] += r.s2.w;
-      float gv[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float2 p0 = Elem<E>::unpack2(r.g[a].x), p1 = Elem<E>::unpack2(r.g[a].y);
-        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
-      }
-      const float cpv[4] = {r.cp.x, r.cp.y, r.cp.z, r.cp.w};
-      const float cnv[4] = {r.cn.x, r.cn.y, r.cn.z, r.cn.w};
-      const float dcv[4] = {r.dc.x, r.dc.y, r.dc.z, r.dc.w};
-      float dzv[4][4], dcn[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
-        const float tc = fast_tanh(cnv[e]);
-        const float d_o = dhv[e] * tc;
-        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
-        dzv[0][e] = dct * gg * gi * (1.f - gi);
-        dzv[1][e] = dct * cpv[e] * gf * (1.f - gf);
-        dzv[2][e] = d_o * go * (1.f - go);
-        dzv[3][e] = dct * gi * (1.f - gg * gg);
-        dcn[e] = dct * gf;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
-      }
+      float4 dcn;
+      uint2 dzp[4];
+      gate_grad_item4<E>(r.g, r.cp, r.cn, r.dc, dhv, bsum, zmax, dcn, dzp);
       const unsigned o4 = r.pix * 256u, o1 = r.pix * 64u + chunk * 4;
-      *reinterpret_cast<float4*>(gw.dc + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+      *reinterpret_cast<float4*>(gw.dc + o1) = dcn;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
-            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+      for (int a = 0; a < 4; ++a) *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) = dzp[a];
     };
     const unsigned stride = gridDim.x * 24u;  // 384 workers = 24 pixels per CTA pass
     unsigned p0 = blockIdx.x * 24u + plane, p1 = p0 + stride;
@@ -205,6 +183,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       p1 += 2 * stride;
       issue(rb, p1);
     }
+    fold_absmax<E>(zmax, gw.dz_absmax);
     float* row = gw.bias_partial + (static_cast<size_t>(blockIdx.x) * 16 + (warp - 8)) * 256;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -277,12 +256,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int w0 = tw * p.BW, h0 = th * p.BH;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* dst = smem + stage * stage_bytes;
-        if (p.dbg_no_tma && it >= p.stages) {
-          if (lane == 0) mbar_arrive(&full_bar[stage]);
-        } else {
-          if (lane == 0) mbar_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_4d(dst + lane * kBoxBytes, map, &full_bar[stage], c0, w0 + dxs, h0 + dys, b + boff);
-        }
+        if (lane == 0) mbar_expect_tx(&full_bar[stage], stage_bytes);
+        tma_load_4d(dst + lane * kBoxBytes, map, &full_bar[stage], c0, w0 + dxs, h0 + dys, b + boff);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -341,6 +316,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
+    uint32_t zmax = 0;
     for (unsigned pix = blockIdx.x * 32u + plane; pix < gw.npix; pix += gridDim.x * 32u) {
       const unsigned o4 = pix * 256u + 0u, o1 = pix * 64u + chunk * 4;
       uint2 g[4];
@@ -362,36 +338,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float4 t = __ldg(reinterpret_cast<const float4*>(gw.src2 + o1));
         dhv[0] += t.x, dhv[1] += t.y, dhv[2] += t.z, dhv[3] += t.w;
       }
-      float gv[4][4];
+      float4 dcn;
+      uint2 dzp[4];
+      gate_grad_item4<E>(g, cp, cn4, dc4, dhv, bsum, zmax, dcn, dzp);
+      *reinterpret_cast<float4*>(gw.dc + o1) = dcn;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float2 p0 = Elem<E>::unpack2(g[a].x), p1 = Elem<E>::unpack2(g[a].y);
-        gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
-      }
-      const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-      const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
-      const float dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
-      float dzv[4][4], dcn[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
-        const float tc = fast_tanh(cnv[e]);
-        const float d_o = dhv[e] * tc;
-        const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
-        dzv[0][e] = dct * gg * gi * (1.f - gi);
-        dzv[1][e] = dct * cpv[e] * gf * (1.f - gf);
-        dzv[2][e] = d_o * go * (1.f - go);
-        dzv[3][e] = dct * gi * (1.f - gg * gg);
-        dcn[e] = dct * gf;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
-      }
-      *reinterpret_cast<float4*>(gw.dc + o1) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) =
-            make_uint2(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]));
+      for (int a = 0; a < 4; ++a) *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) = dzp[a];
     }
+    fold_absmax<E>(zmax, gw.dz_absmax);
     // bias partial sums: add the warp's two pixel lanes, one row of bias_partial per worker warp (fixed order)
     float* row = gw.bias_partial + (static_cast<size_t>(blockIdx.x) * 16 + (warp - 8)) * 256;
 #pragma unroll

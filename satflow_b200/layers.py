@@ -26,18 +26,26 @@ def get_conv_layer(conv_type: str = "standard"):
 
 
 class _CellFn(torch.autograd.Function):
+    """One cell step.  The activations its backward needs (packed x / h / c, gates, packed weights) live in a
+    ``saved`` device region owned by THIS node, so a chain of steps through the same cell back-propagates correctly."""
+
     @staticmethod
     def forward(ctx, plan, x, h, c, weight, bias):
-        hn, cn = plan.forward(x, h, c, weight, bias)
+        needs_grad = any(ctx.needs_input_grad[1:])
+        hn, cn, saved = plan.forward(x, h, c, weight, bias, keep=needs_grad)
         ctx.plan = plan
         ctx.has_bias = bias is not None
+        ctx.saved_region = saved if needs_grad else None
         ctx.save_for_backward(weight)
         return hn, cn
 
     @staticmethod
     def backward(ctx, dh, dc):
         (weight,) = ctx.saved_tensors
-        dx, dhp, dcp, dw, db = ctx.plan.backward(dh, dc, weight, need_bias=ctx.has_bias)
+        if ctx.saved_region is None:  # pragma: no cover - autograd only calls backward when something needed a gradient
+            raise RuntimeError("satflow_b200.ConvLSTMCell: backward of a forward that ran without gradient tracking")
+        dx, dhp, dcp, dw, db = ctx.plan.backward(ctx.saved_region, dh, dc, weight, need_bias=ctx.has_bias)
+        ctx.saved_region = None  # single use: release the activations
         return None, dx, dhp, dcp, dw, db
 
 

@@ -68,7 +68,17 @@ class RolloutPlan:
             _lib.check(
                 L.clstm_plan_bind(self._h, _lib.ptr(self.workspace), self.workspace_bytes, _stream_ptr(self.device))
             )
-        self._weights_key = None
+        # forward/backward pairing (autograd): every forward gets a new generation; a backward must present the
+        # generation of the forward whose saved states are still in the workspace
+        self.generation = 0
+        self.pending_backward = False
+        # gradient range statistics of the last backwards (include/clstm.h clstm_plan_grad_status), fetched without
+        # synchronising: a small ring of pinned host slots, each guarded by an event
+        self.overflow_policy = "raise"  # "raise" | "ignore"
+        self._status_dev = None
+        self._status_host = None
+        self._status_slots = []  # (slot index, event, generation)
+        self.last_grad_status = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -82,13 +92,12 @@ class RolloutPlan:
         except Exception:
             pass
 
-    def set_weights(self, params: Sequence[torch.Tensor], force: bool = False) -> None:
-        """params in the order of include/clstm.h clstm_plan_set_weights; repacks only when they changed."""
+    def set_weights(self, params: Sequence[torch.Tensor]) -> None:
+        """params in the order of include/clstm.h clstm_plan_set_weights.  Repacked on EVERY call (a few microseconds
+        of device time): writes through ``p.data`` — the reference's ``init_weights`` (gan/common.py:44-50), WGAN
+        weight clipping, ``load_state_dict`` — do not bump ``p._version``, so no cache key can be trusted."""
         if len(params) != self.n_params:
             raise ValueError(f"expected {self.n_params} parameter tensors, got {len(params)}")
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if not force and key == self._weights_key:
-            return
         for i, p in enumerate(params):
             _require_cuda(p, f"parameter {i}")
             if not p.is_contiguous():
@@ -99,10 +108,58 @@ class RolloutPlan:
                     self._h, _lib.ptr_array(list(params)), len(params), _stream_ptr(self.device)
                 )
             )
-        self._weights_key = key
+
+    # ---- gradient range statistics ------------------------------------------------------------------------
+    _STATUS_RING = 4
+
+    def _capture_grad_status(self) -> None:
+        if self._status_dev is None:
+            self._status_dev = torch.empty(self._STATUS_RING, 4, dtype=torch.float32, device=self.device)
+            self._status_host = torch.empty(self._STATUS_RING, 4, dtype=torch.float32).pin_memory()
+        if len(self._status_slots) >= self._STATUS_RING:  # ring full: the oldest entry must be consumed first
+            self.poll_grad_status(block=True)
+        used = {s for s, _, _ in self._status_slots}
+        slot = next(i for i in range(self._STATUS_RING) if i not in used)
+        _lib.check(_lib.lib().clstm_plan_grad_status(self._h, _lib.ptr(self._status_dev[slot]), _stream_ptr(self.device)))
+        self._status_host[slot].copy_(self._status_dev[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._status_slots.append((slot, ev, self.generation))
+
+    def poll_grad_status(self, block: bool = False):
+        """Consume the statistics of finished backwards (``block``: wait for all of them).  Raises
+        ``FloatingPointError`` when a 16-bit gradient operand overflowed (policy "raise"); returns the newest dict
+        ``{"scale", "amax_dlogit", "amax_dz_scaled", "headroom_log2", "generation"}`` or None."""
+        import math
+
+        while self._status_slots:
+            slot, ev, gen = self._status_slots[0]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            self._status_slots.pop(0)
+            S, _, a_dl, a_dz = (float(v) for v in self._status_host[slot])
+            limit = 65504.0 if self.cfg.dtype == _lib.CLSTM_F16 else 3.0e38
+            st = {"scale": S, "amax_dlogit": a_dl, "amax_dz_scaled": a_dz, "generation": gen,
+                  "headroom_log2": (math.log2(limit / a_dz) if 0.0 < a_dz < float("inf") else
+                                    (float("-inf") if a_dz > 0.0 else float("inf")))}
+            self.last_grad_status = st
+            if not (a_dz < float("inf")) or not (a_dl < float("inf")):
+                if self.overflow_policy == "raise":
+                    what = "the loss gradient dy is not finite" if not (a_dl < float("inf")) else (
+                        "a 16-bit gradient operand overflowed during back-propagation through time "
+                        f"(loss scale {S:g}, max |dlogit| {a_dl:g})")
+                    raise FloatingPointError(
+                        f"satflow_b200: {what} in the backward of forward #{gen}; the gradients of that step are not "
+                        "usable (skip the optimizer step; clip the weights / lower the learning rate, or pass a smaller "
+                        "fixed grad_scale)")
+        return self.last_grad_status
 
     def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, channels_last: bool = False) -> torch.Tensor:
         c = self.cfg
+        if self._status_slots:
+            self.poll_grad_status(block=False)  # surfaces an overflow of an earlier backward; never waits
         _require_cuda(x, "x")
         want = ((c.batch, c.t_in, c.height, c.width, c.in_channels) if channels_last
                 else (c.batch, c.t_in, c.in_channels, c.height, c.width))
@@ -117,11 +174,23 @@ class RolloutPlan:
                     self._h, _lib.ptr(x), 1 if channels_last else 0, _lib.ptr(y), _stream_ptr(self.device)
                 )
             )
+        self.generation += 1
+        self.pending_backward = self.training
         return y
 
-    def backward(self, dy: torch.Tensor, y: torch.Tensor, grads: Sequence[Optional[torch.Tensor]], accumulate: bool = False):
+    def backward(self, dy: torch.Tensor, y: torch.Tensor, grads: Sequence[Optional[torch.Tensor]], accumulate: bool = False,
+                 generation: Optional[int] = None):
+        """``generation``: the value of ``self.generation`` right after the forward this backward belongs to; a
+        mismatch means a later forward on the same plan has overwritten the saved gates / states."""
+        if generation is not None and generation != self.generation:
+            raise RuntimeError(
+                "satflow_b200: backward of a rollout whose saved activations were overwritten by a later forward on the "
+                f"same plan (forward generation {generation}, plan is at {self.generation}).  Run backward before the "
+                "next forward of the same shape, or wrap the intermediate forward in torch.no_grad()."
+            )
         _require_cuda(dy, "dy")
         dy = dy.contiguous()
+        y = y.contiguous()
         with torch.cuda.device(self.device):
             _lib.check(
                 _lib.lib().clstm_rollout_backward(
@@ -129,6 +198,9 @@ class RolloutPlan:
                     _stream_ptr(self.device),
                 )
             )
+            if self.overflow_policy != "ignore":
+                self._capture_grad_status()
+        self.pending_backward = False
 
     KERNELS = {"cell_fwd": 0, "gate_grad": 1, "dgrad": 2, "wgrad": 3, "wgrad+gate_grad": 4, "dgrad_fused": 5}
 
@@ -154,7 +226,13 @@ class RolloutPlan:
 
 
 class CellPlan:
-    """clstm_cell_plan_t: one ConvLSTMCell.forward shape (layers/ConvLSTM.py:42-57)."""
+    """clstm_cell_plan_t: one ConvLSTMCell.forward shape (layers/ConvLSTM.py:42-57).
+
+    The plan's memory is two regions (include/clstm.h clstm_cell_plan_bind_split): ``scratch`` is owned here and
+    reused by every call; the ``saved`` region — packed inputs, states and gates that the backward reads — belongs to
+    ONE forward call.  A forward that may be differentiated gets a fresh saved region which travels with its autograd
+    node, so unrolling the cell over T steps (the reference's usage, conv_lstm.py:176-196) and back-propagating
+    through all of them is correct; forwards under ``torch.no_grad()`` share one."""
 
     def __init__(self, batch, height, width, in_channels, hidden, kernel_size=(3, 3), dtype="fp16", device=None):
         L = _lib.lib()
@@ -168,17 +246,20 @@ class CellPlan:
                     ctypes.byref(self._h),
                 )
             )
-            self.workspace_bytes = int(L.clstm_cell_plan_workspace_bytes(self._h))
-            self.workspace = _aligned_workspace(self.workspace_bytes, self.device)
-            _lib.check(
-                L.clstm_cell_plan_bind(self._h, _lib.ptr(self.workspace), self.workspace_bytes, _stream_ptr(self.device))
-            )
+            self.saved_bytes = int(L.clstm_cell_plan_saved_bytes(self._h))
+            self.scratch_bytes = int(L.clstm_cell_plan_scratch_bytes(self._h))
+            self.workspace_bytes = self.saved_bytes + self.scratch_bytes
+            self.scratch = _aligned_workspace(self.scratch_bytes, self.device)
+        self._shared_saved = None  # saved region of the no-grad forwards
+        self._bound = None  # the saved region the plan's tensor maps currently point at
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             _lib.lib().clstm_cell_plan_destroy(self._h)
             self._h = None
-            self.workspace = None
+            self.scratch = None
+            self._shared_saved = None
+            self._bound = None
 
     def __del__(self):  # pragma: no cover
         try:
@@ -186,35 +267,61 @@ class CellPlan:
         except Exception:
             pass
 
-    def forward(self, x, h, c, weight, bias):
+    def _bind(self, saved: torch.Tensor) -> None:
+        if self._bound is saved:
+            return
+        _lib.check(
+            _lib.lib().clstm_cell_plan_bind_split(
+                self._h, _lib.ptr(saved), self.saved_bytes, _lib.ptr(self.scratch), self.scratch_bytes,
+                _stream_ptr(self.device),
+            )
+        )
+        self._bound = saved
+
+    def forward(self, x, h, c, weight, bias, keep: bool = True):
+        """Returns (h_next, c_next, saved).  ``keep``: the call may be differentiated -> it gets its own saved region
+        (hand it back to :meth:`backward`)."""
         for name, t in (("x", x), ("h", h), ("c", c), ("weight", weight)):
             _require_cuda(t, name)
         B, H, W, _, hid = self.shape
+        # contiguous copies stay referenced until the launch is enqueued: a temporary's block could otherwise be handed
+        # to the next .contiguous() by the caching allocator and two operands would alias
+        xc, hc, cc, wc = x.contiguous(), h.contiguous(), c.contiguous(), weight.contiguous()
+        bc = None if bias is None else bias.contiguous()
         hn = torch.empty(B, hid, H, W, dtype=torch.float32, device=x.device)
         cn = torch.empty_like(hn)
         with torch.cuda.device(self.device):
+            if keep:
+                saved = _aligned_workspace(self.saved_bytes, self.device)
+            else:
+                if self._shared_saved is None:
+                    self._shared_saved = _aligned_workspace(self.saved_bytes, self.device)
+                saved = self._shared_saved
+            self._bind(saved)
             _lib.check(
                 _lib.lib().clstm_cell_forward(
-                    self._h, _lib.ptr(x.contiguous()), _lib.ptr(h.contiguous()), _lib.ptr(c.contiguous()),
-                    _lib.ptr(weight.contiguous()), _lib.ptr(None if bias is None else bias.contiguous()),
-                    _lib.ptr(hn), _lib.ptr(cn), _stream_ptr(self.device),
+                    self._h, _lib.ptr(xc), _lib.ptr(hc), _lib.ptr(cc), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(hn),
+                    _lib.ptr(cn), _stream_ptr(self.device),
                 )
             )
-        return hn, cn
+        return hn, cn, saved
 
-    def backward(self, dh, dc, weight, need_bias=True):
+    def backward(self, saved, dh, dc, weight, need_bias=True):
         B, H, W, cin, hid = self.shape
         dev = self.device
         dx = torch.empty(B, cin, H, W, dtype=torch.float32, device=dev)
         dhp = torch.empty(B, hid, H, W, dtype=torch.float32, device=dev)
         dcp = torch.empty_like(dhp)
-        dw = torch.empty_like(weight)
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
         db = torch.empty(4 * hid, dtype=torch.float32, device=dev) if need_bias else None
+        dhc = None if dh is None else dh.contiguous()
+        dcc = None if dc is None else dc.contiguous()
+        wc = weight.contiguous()
         with torch.cuda.device(self.device):
+            self._bind(saved)
             _lib.check(
                 _lib.lib().clstm_cell_backward(
-                    self._h, _lib.ptr(None if dh is None else dh.contiguous()),
-                    _lib.ptr(None if dc is None else dc.contiguous()), _lib.ptr(weight), _lib.ptr(dx), _lib.ptr(dhp),
+                    self._h, _lib.ptr(dhc), _lib.ptr(dcc), _lib.ptr(wc), _lib.ptr(dx), _lib.ptr(dhp),
                     _lib.ptr(dcp), _lib.ptr(dw), _lib.ptr(db), _stream_ptr(self.device),
                 )
             )

@@ -82,8 +82,10 @@ def cell_golden(name: str, dtype="fp16") -> Dict[str, float]:
 
 
 def rollout_case(B, tin, tout, cin, hid, cout, H, W, n_layers=2, k=3, dtype="fp16", weight_scale=1.0, seed=0,
-                 backward=True, states=True) -> Dict[str, float]:
-    """CUDA rollout (module API -> C ABI) vs the oracle on the same seeded inputs and weights."""
+                 backward=True, states=True, loss_scale=1.0, status=None) -> Dict[str, float]:
+    """CUDA rollout (module API -> C ABI) vs the oracle on the same seeded inputs and weights.  ``loss_scale``
+    multiplies the loss on both sides (gradient range tests); ``status`` (a dict) receives the range statistics of
+    the device backward."""
     from satflow_b200 import ConvLSTM
 
     g = torch.Generator().manual_seed(1234 + seed)
@@ -98,9 +100,12 @@ def rollout_case(B, tin, tout, cin, hid, cout, H, W, n_layers=2, k=3, dtype="fp1
     if backward:
         y = net(x.cuda(), tout)
         loss = torch.nn.functional.mse_loss(y.permute(0, 2, 1, 3, 4), tgt.cuda())
-        loss.backward()
+        (loss * loss_scale).backward()
+        st = net.check_gradients()  # raises FloatingPointError on a 16-bit overflow
+        if status is not None and st is not None:
+            status.update(st)
         loss_o, dy_o = O.mse_loss_and_grad(y_o, tgt)
-        g_o = O.rollout_backward(dy_o, sv, p)
+        g_o = O.rollout_backward(dy_o * loss_scale, sv, p)
         out["loss"] = abs(loss.item() - loss_o.item()) / abs(loss_o.item())
         for name, prm in net.named_parameters():
             out["grad." + name] = rel(prm.grad, g_o[name])
@@ -142,4 +147,100 @@ def rollout_golden(name: str, dtype="fp16") -> Dict[str, float]:
     for k, prm in lit.named_parameters():
         out["grad." + k] = rel(prm.grad, z["grad." + k])
     lit.model.release_plans()
+    return out
+
+
+def cell_unrolled_case(B, cin, hid, H, W, steps, k=3, seed=0) -> Dict[str, float]:
+    """The reference's ONLY way of using the cell (conv_lstm.py:176-183): the same ConvLSTMCell applied ``steps``
+    times, h/c threaded through, then loss.backward() through all of them.  Every step's gradient contributes to the
+    shared weight, so each autograd node must own its saved activations."""
+    from satflow_b200 import ConvLSTMCell
+
+    g = torch.Generator().manual_seed(77 + seed)
+    torch.manual_seed(2000 + seed)
+    cell = ConvLSTMCell(cin, hid, (k, k), True)
+    xs = torch.randn(steps, B, cin, H, W, generator=g)
+    wsum = torch.randn(steps, B, hid, H, W, generator=g)  # loss = sum_t <h_t, wsum_t> + <c_T, wsum_0>
+    w = cell.conv.weight.detach().clone()
+    b = cell.conv.bias.detach().clone()
+    # oracle (autograd through the restated cell)
+    wo, bo = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xo = xs.clone().requires_grad_(True)
+    h = torch.zeros(B, hid, H, W)
+    c = torch.zeros(B, hid, H, W)
+    loss_o = 0.0
+    for t in range(steps):
+        h, c, _ = O.cell_forward(xo[t], h, c, wo, bo)
+        loss_o = loss_o + (h * wsum[t]).sum()
+    loss_o = loss_o + (c * wsum[0]).sum()
+    loss_o.backward()
+    # device
+    cell = cell.cuda()
+    xg = xs.cuda().requires_grad_(True)
+    hg, cg = cell.init_hidden(B, (H, W))
+    loss = 0.0
+    wg = wsum.cuda()
+    for t in range(steps):
+        hg, cg = cell(xg[t], [hg, cg])
+        loss = loss + (hg * wg[t]).sum()
+    loss = loss + (cg * wg[0]).sum()
+    loss.backward()
+    return {
+        "h_T": rel(hg, h), "c_T": rel(cg, c), "loss": abs(loss.item() - loss_o.item()) / abs(loss_o.item()),
+        "dx": rel(xg.grad, xo.grad), "dweight": rel(cell.conv.weight.grad, wo.grad),
+        "dbias": rel(cell.conv.bias.grad, bo.grad),
+    }
+
+
+def cloudgan_generator_case(B=2, tin=3, tout=4, cin=12, hid=16, cout=12, H=16, W=24) -> Dict[str, float]:
+    """What CloudGAN does to a ConvLSTM generator (cloudgan.py:88-92, gan/generators.py:49-50,69, gan/common.py:44-64):
+    build it with keyword arguments, run it once, RE-INITIALISE every Conv weight through ``m.weight.data`` (which does
+    not bump the autograd version counter), run it again and slice the (B, C, T, H, W) output per time step
+    (cloudgan.py:147,176,291).  The second forward must see the new weights."""
+    from torch.nn import init
+
+    from satflow_b200 import ConvLSTM
+
+    torch.manual_seed(31)
+    net = ConvLSTM(cin, hidden_dim=hid, out_channels=cout).cuda()
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(B, tin, cin, H, W, generator=g)
+    with torch.no_grad():
+        y_before = net(x.cuda(), forecast_steps=tout).clone()
+
+    def init_func(m):  # gan/common.py:44-64, init_type "normal", gain 0.02
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            init.normal_(m.weight.data, 0.0, 0.02)
+            if hasattr(m, "bias") and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+
+    net.apply(init_func)
+    p = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    y_o, sv = O.rollout_forward(x, p, tout)
+    out: Dict[str, float] = {}
+    with torch.no_grad():
+        y = net(x.cuda(), forecast_steps=tout)
+    out["y_after_reinit"] = rel(y, y_o)
+    yc = y.detach().cpu().double().clamp(1e-12, 1 - 1e-12)
+    out["logits_after_reinit"] = rel(torch.log(yc / (1 - yc)).float(), sv.logits)
+    out["changed"] = 0.0 if float((y - y_before).abs().max()) > 1e-4 else 1.0  # 1.0 = stale weights were used
+    for i in range(tout):  # consumers slice generated_images[:, :, i, :, :]
+        out[f"slice[{i}]"] = rel(y[:, :, i, :, :], y_o[:, :, i, :, :])
+    # a generator step: loss through a "discriminator" (here a fixed random projection) and backward; then an in-place
+    # .data update (WGAN weight clipping style) followed by another forward
+    tgt = torch.rand(B, tout, cout, H, W, generator=g)
+    yg = net(x.cuda(), forecast_steps=tout)
+    torch.nn.functional.mse_loss(yg.permute(0, 2, 1, 3, 4), tgt.cuda()).backward()
+    loss_o, dy_o = O.mse_loss_and_grad(y_o, tgt)
+    g_o = O.rollout_backward(dy_o, sv, p)
+    for name, prm in net.named_parameters():
+        out["grad." + name] = rel(prm.grad, g_o[name])
+    for prm in net.parameters():
+        prm.data.clamp_(-0.01, 0.01)
+    p2 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    y2_o, _ = O.rollout_forward(x, p2, tout)
+    with torch.no_grad():
+        out["y_after_clip"] = rel(net(x.cuda(), forecast_steps=tout), y2_o)
+    net.release_plans()
     return out

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(_lib.exported_symbols()) == declared
-    assert L.clstm_abi_version() == 1
+    assert L.clstm_abi_version() == 2
 
 
 def _create(**kw):
