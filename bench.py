@@ -3,6 +3,9 @@
 
   python bench.py --gpus N --steps K --warmup W              our arm (one process per GPU; torchrun for N>1)
   python bench.py --impl reference --gpus N --steps K ...    the reference's CPU implementation of the same path
+  python bench.py --impl eager-gpu                           informational: the same torch ops on the GPU (cuDNN, TF32)
+  python bench.py --gpus N --check                           N-GPU sharded gradients == 1-GPU full-batch gradients
+  python bench.py --gpus N --global-batch 128                strong-scaling form of BASELINE configs[2] (micro-batches)
 
 One step = zero_grad + forward rollout + MSE loss + backward (BPTT) + gradient all-reduce (N>1) + Adam step
 on one batch of synthetic 12-channel sequences, hid 64, 256x256, 12 in / 24 out, batch 16 per GPU (weak scaling;
@@ -12,8 +15,10 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -28,6 +33,8 @@ import torch  # noqa: E402
 
 METRIC = "ConvLSTM rollout frames/s (fwd+bwd)"
 CFG = dict(hidden=64, channels=12, out_channels=12, hw=256, t_in=12, t_out=24, batch_per_gpu=16)
+# the bounded sample of the workload that the CPU legs time (frames/s is normalised by B * (t_in + t_out))
+CPU_SAMPLE = dict(batch=1, t_in=4, t_out=8)
 
 
 def algorithmic_flops_fwd(B, t_in, t_out, cin, hid, cout, H, W, k=3, n_layers=2):
@@ -52,6 +59,32 @@ def measured_peaks():
         return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, read from the committed
+    `ncu --set full` summary (tools/ncu_summary.py output under profiles/); (None, None) if no capture is committed."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name in ("r2_ncu_full_summary.csv", "r1_v2_ncu_full_summary.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(path):
+            continue
+        vals = []
+        with open(path) as f:
+            for row in csv.DictReader(f):
+                if kernel_substr not in row.get("kernel", ""):
+                    continue
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    m = re.match(r"([0-9.]+)\s*(\w+)", row.get(key, ""))
+                    if not m:
+                        break
+                    tot += float(m.group(1)) * unit.get(m.group(2), 1.0)
+                else:
+                    vals.append(tot)
+        if vals:
+            return sum(vals) / len(vals), f"profiles/{name} ({len(vals)} launch(es), ncu --set full)"
+    return None, None
 
 
 class ClockSampler:
@@ -102,7 +135,7 @@ def cpu_reference_sample(steps: int, warmup: int, threads: int):
     from oracle import convlstm_oracle as O
 
     torch.set_num_threads(threads)
-    B, t_in, t_out = 1, 4, 8
+    B, t_in, t_out = CPU_SAMPLE["batch"], CPU_SAMPLE["t_in"], CPU_SAMPLE["t_out"]
     g = torch.Generator().manual_seed(1234)
     p = {k: v.requires_grad_(True) for k, v in O.init_params(CFG["channels"], CFG["hidden"], CFG["out_channels"], seed=0).items()}
     x = torch.randn(B, t_in, CFG["channels"], CFG["hw"], CFG["hw"], generator=g)
@@ -123,62 +156,231 @@ def cpu_reference_sample(steps: int, warmup: int, threads: int):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=B * (t_in + t_out) / dt, ms_per_step=dt * 1e3,
-                sample=f"B=1, {t_in} in / {t_out} out, hid {CFG['hidden']}, {CFG['hw']}x{CFG['hw']}, fwd+bwd+Adam, "
-                       f"{steps} timed steps after {warmup} warm-up (torch {torch.__version__} CPU fp32)")
+    return dict(value=B * (t_in + t_out) / dt, ms_per_step=dt * 1e3, threads=torch.get_num_threads(),
+                sample=f"B={B}, {t_in} in / {t_out} out, hid {CFG['hidden']}, {CFG['hw']}x{CFG['hw']}, fwd+bwd+Adam, "
+                       f"{steps} timed steps after {warmup} warm-up (torch {torch.__version__} CPU fp32, "
+                       f"{torch.get_num_threads()} threads)")
+
+
+def sample_workload():
+    s = CPU_SAMPLE
+    return (f"BOUNDED SAMPLE of the workload below, timed per step: batch {s['batch']}, {s['t_in']} in / {s['t_out']} out "
+            f"(same hid {CFG['hidden']}, {CFG['channels']}ch, {CFG['hw']}x{CFG['hw']}, fwd+bwd+Adam); frames/s = "
+            f"B*(T_in+T_out)/t is per-frame normalised, so it compares with the full configuration: ")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this leg is meant to use every host core
     threads = os.cpu_count() or 1
     r = cpu_reference_sample(max(1, args.steps), max(1, min(args.warmup, 1)), threads)
+    cfg = workload_config(args.gpus)
+    cfg["workload"] = sample_workload() + cfg["workload"]
+    cfg["sample"] = dict(CPU_SAMPLE)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+        "config": cfg,
+        "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def workload_config(n):
-    return {
+def cpu_baseline_subprocess():
+    """The cpu_baseline leg of our arm: the reference arm run as a child process with a clean threading environment
+    (no OMP_NUM_THREADS / MKL_NUM_THREADS inherited from a launcher), one timed step after one warm-up."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE", "CUDA_VISIBLE_DEVICES")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+        return d["cpu_baseline"]
+    except Exception as e:  # the baseline is a reported number, not a dependency of the measurement
+        return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+
+def workload_config(n, global_batch=None):
+    per = CFG["batch_per_gpu"]
+    d = {
         "workload": (f"encoder-forecaster ConvLSTM (2 enc + 2 dec cells, 3x3) hid {CFG['hidden']}, {CFG['channels']}ch "
-                     f"{CFG['hw']}x{CFG['hw']}, {CFG['t_in']} in / {CFG['t_out']} out, batch {CFG['batch_per_gpu']}/GPU, "
+                     f"{CFG['hw']}x{CFG['hw']}, {CFG['t_in']} in / {CFG['t_out']} out, batch {per}/GPU, "
                      "fwd+bwd+grad-allreduce+Adam (BASELINE configs[2]; shape of configs[1])"),
-        "global_batch": CFG["batch_per_gpu"] * n, "parallelism": f"dp{n}",
+        "global_batch": per * n, "parallelism": f"dp{n}",
         "l2": "working set (71 GB of saved states per step) >> 126 MB L2; no flush needed",
     }
+    if global_batch:
+        d["global_batch"] = global_batch
+        d["micro_batches_per_gpu"] = global_batch // (n * per)
+        d["workload"] = d["workload"].replace(f"batch {per}/GPU", f"global batch {global_batch} = {global_batch // n}/GPU in "
+                                              f"micro-batches of {per} with gradient accumulation")
+    return d
+
+
+# ------------------------------------------------------------------------------------------ informational GPU-eager arm
+def run_eager_gpu(args):
+    """SURVEY.md §0 names PyTorch eager (cuDNN conv + ATen pointwise) on the same B200 as the bar: the oracle's op
+    sequence (= the reference's) on the GPU with torch's defaults for convolutions (cudnn.allow_tf32 = True), largest
+    batch that fits next to autograd's saved activations.  Informational; not part of the driver's contract."""
+    from oracle import convlstm_oracle as O
+
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    t_in, t_out = CFG["t_in"], CFG["t_out"]
+    res = None
+    for B in (16, 8, 4, 2, 1):
+        try:
+            g = torch.Generator().manual_seed(1234)
+            p = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params(CFG["channels"], CFG["hidden"], CFG["out_channels"], seed=0).items()}
+            x = torch.randn(B, t_in, CFG["channels"], CFG["hw"], CFG["hw"], generator=g).to(dev)
+            tgt = torch.rand(B, t_out, CFG["out_channels"], CFG["hw"], CFG["hw"], generator=g).to(dev)
+            opt = torch.optim.Adam(list(p.values()), lr=1e-4, fused=True)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                y, _ = O.rollout_forward(x, p, t_out)
+                loss = torch.nn.functional.mse_loss(y.permute(0, 2, 1, 3, 4), tgt)
+                loss.backward()
+                opt.step()
+
+            for _ in range(max(2, args.warmup)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            with torch.no_grad():
+                for _ in range(2):
+                    O.rollout_forward(x, p, t_out)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(args.steps):
+                    O.rollout_forward(x, p, t_out)
+                e1.record()
+                torch.cuda.synchronize()
+            ms_inf = e0.elapsed_time(e1) / args.steps
+            res = dict(batch=B, ms_per_step=ms, frames_per_s=B * (t_in + t_out) / ms * 1e3,
+                       inference_ms=ms_inf, inference_frames_per_s=B * (t_in + t_out) / ms_inf * 1e3,
+                       peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
+            break
+        except torch.OutOfMemoryError:
+            del p, x, tgt
+            torch.cuda.empty_cache()
+    emit({"impl": "eager-gpu", "metric": METRIC, "value": res["frames_per_s"] if res else None, "unit": "frames/s",
+          "n_gpus": 1, "dtype": "tf32 conv (cudnn.allow_tf32) / fp32 pointwise", "data": "synthetic",
+          "config": workload_config(1), "result": res,
+          "note": "torch eager: cat -> cuDNN Conv2d -> split -> sigmoid/tanh -> ... with autograd, fused Adam"})
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def setup_dist(args):
     import torch.distributed as dist
-
-    from satflow_b200 import EncoderDecoderConvLSTM, _lib
-    from satflow_b200.distributed import FlatGradBucket, broadcast_parameters
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun (--nproc-per-node {args.gpus})")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun (--nproc-per-node {args.gpus})")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    return dist, world, rank, local, dev
+
+
+def run_check(args):
+    """Multi-GPU correctness on hardware: (1) gradients of a global batch sharded over N ranks and
+    averaged by the one all-reduce == the gradients one GPU computes on the whole batch (rel-L2 <= 2e-3 per tensor);
+    (2) after the Adam step every replica holds bit-identical parameters."""
+    from satflow_b200 import EncoderDecoderConvLSTM
+    from satflow_b200.distributed import FlatGradBucket, broadcast_parameters, shard_batch
+
+    dist, world, rank, local, dev = setup_dist(args)
+    per, t_in, t_out, hw = 2, 4, 6, 64
+    G = per * world
+    torch.manual_seed(0)
+    model = EncoderDecoderConvLSTM(hidden_dim=64, input_channels=12, out_channels=12, forecast_steps=t_out, lr=1e-3).to(dev)
+    broadcast_parameters(model)
+    g = torch.Generator().manual_seed(99)
+    x_all = torch.randn(G, t_in, 12, hw, hw, generator=g).to(dev)
+    y_all = torch.rand(G, t_out, 12, hw, hw, generator=g).to(dev)
+    bucket = FlatGradBucket(model.parameters())
+    # 1-GPU full-batch gradients (every rank computes them: same data, same weights)
+    bucket.zero_()
+    model.training_step((x_all, y_all), 0).backward()
+    full = bucket.flat.clone()
+    # sharded
+    bucket.zero_()
+    model.training_step((shard_batch(x_all, rank, world).contiguous(), shard_batch(y_all, rank, world).contiguous()), 0).backward()
+    bucket.all_reduce_mean()
+    worst, off = 0.0, 0
+    for p_ in bucket.params:
+        n = p_.numel()
+        a, b = bucket.flat[off:off + n], full[off:off + n]
+        worst = max(worst, float((a - b).norm() / b.norm().clamp_min(1e-30)))
+        off += n
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    opt.step()
+    flat_p = torch.cat([p_.detach().reshape(-1) for p_ in model.parameters()])
+    ident = True
+    if world > 1:
+        ref = flat_p.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1.0 if torch.equal(ref, flat_p) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ident = bool(same.item() == 1.0)
+        w = torch.tensor([worst], device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        worst = float(w.item())
+    ok = worst <= 2e-3 and ident
+    if rank == 0:
+        emit({"check": "multi-gpu gradient equivalence", "n_gpus": world, "ok": ok, "worst_rel_l2_vs_full_batch": worst,
+              "replicas_bit_identical_after_adam": ident, "tolerance": 2e-3,
+              "config": {"workload": f"hid 64, 12ch {hw}x{hw}, {t_in} in / {t_out} out, global batch {G} = {per}/GPU"}})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not ok:
+        raise SystemExit(1)
+
+
+def parse_trace(report: str):
+    """clstm_trace_report table -> {kernel name: (count, total ms, avg us)}."""
+    out = {}
+    for ln in report.splitlines():
+        m = re.match(r"\s*([0-9.]+) ms\s+[0-9.]+%\s+n=\s*(\d+)\s+avg=\s*([0-9.]+) us\s+(.*)$", ln)
+        if m:
+            out[m.group(4).strip()] = (int(m.group(2)), float(m.group(1)), float(m.group(3)))
+    return out
+
+
+def run_ours(args):
+    from satflow_b200 import ConvLSTM, ConvLSTMCell, EncoderDecoderConvLSTM, _lib
+    from satflow_b200.distributed import FlatGradBucket, broadcast_parameters
+
+    dist, world, rank, local, dev = setup_dist(args)
     L = _lib.lib()
     _lib.check(L.clstm_device_check(local))
 
     B, t_in, t_out = CFG["batch_per_gpu"], CFG["t_in"], CFG["t_out"]
     C, Co, hid, HW = CFG["channels"], CFG["out_channels"], CFG["hidden"], CFG["hw"]
+    n_micro = 1
+    if args.global_batch:
+        if args.global_batch % (world * B):
+            raise SystemExit(f"--global-batch must be a multiple of {world * B}")
+        n_micro = args.global_batch // (world * B)
     torch.manual_seed(0)
     model = EncoderDecoderConvLSTM(hidden_dim=hid, input_channels=C, out_channels=Co, forecast_steps=t_out, lr=1e-4)
     model.model.operand_dtype = args.dtype
@@ -187,14 +389,17 @@ def run_ours(args):
     bucket = FlatGradBucket(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, t_in, C, HW, HW, generator=g).pin_memory()
-    y_host = torch.rand(B, t_out, Co, HW, HW, generator=g).pin_memory()
+    x_host = torch.randn(n_micro * B, t_in, C, HW, HW, generator=g).pin_memory()
+    y_host = torch.rand(n_micro * B, t_out, Co, HW, HW, generator=g).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def train_step(x, tgt):
         bucket.zero_()
-        loss = model.training_step((x, tgt), 0)  # conv_lstm.py:53-70: forward, MSE loss, per-frame losses
-        loss.backward()
+        loss = None
+        for m in range(n_micro):  # micro-batches of 16 accumulate into .grad (autograd's +=); mean over the local batch
+            xm, tm = x[m * B:(m + 1) * B], tgt[m * B:(m + 1) * B]
+            loss = model.training_step((xm, tm), 0)  # conv_lstm.py:53-70: forward, MSE loss, per-frame losses
+            (loss / n_micro if n_micro > 1 else loss).backward()
         bucket.all_reduce_mean()
         opt.step()
         return loss
@@ -204,6 +409,13 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
 
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize; device time via CUDA events; max over ranks."""
@@ -215,12 +427,7 @@ def run_ours(args):
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms / steps, (L.clstm_launch_count() - n0)
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, (L.clstm_launch_count() - n0)
 
     for _ in range(max(3, args.warmup)):
         train_step(x_dev, y_dev)
@@ -251,32 +458,75 @@ def run_ours(args):
     e2e_run(args.steps)
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item()
-    ms_e2e /= args.steps
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # inference (BASELINE configs[1]): forward rollout only, same shapes
     extra = {}
-    if rank == 0 or world > 1:
-        def infer():
-            with torch.no_grad():
-                model(x_dev, t_out)
-        for _ in range(3):
-            infer()
-        ms_inf, _ = timed(infer, args.steps)
-        extra["inference"] = {"frames_per_s": world * B * (t_in + t_out) / ms_inf * 1e3, "ms_per_step": ms_inf,
-                              "tflops": algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW) / ms_inf / 1e9}
 
-    # roofline of the dominant kernel (the fused cell step or the fused dgrad + gate-gradient launch, whichever takes
-    # the larger share of the step), timed alone with CUDA events on the launching stream through the C-ABI
-    # measurement hook; the other kernels of the step alongside.
+    def infer():
+        with torch.no_grad():
+            model(x_dev[:B], t_out)
+
+    for _ in range(3):
+        infer()
+    ms_inf, _ = timed(infer, args.steps)
+    extra["inference"] = {"frames_per_s": world * B * (t_in + t_out) / ms_inf * 1e3, "ms_per_step": ms_inf,
+                          "tflops": algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW) / ms_inf / 1e9,
+                          "config": "BASELINE configs[1]: fwd only, batch 16 per GPU"}
+
     peaks = measured_peaks()
     roof = None
     cpu = None
     if rank == 0:
+        fl = cell_step_flops(B, hid, hid, HW, HW)  # a cell step with a 64-channel input: K = (64 + 64) * 9
+        npix = B * HW * HW
+        gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
+        # (1) IN SITU: one CUDA event after every library launch of two more training steps (clstm_trace_enable), i.e.
+        # each kernel's average duration under the clocks and cache state of the real step -> sustained peak.
+        _lib.trace_enable(4096)
+        for _ in range(2):
+            train_step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        tr = parse_trace(_lib.trace_report())
+        _lib.trace_enable(0)
+        tensor_kernels = {
+            "cell_step": ("convgemm_kernel<EPI_LSTM>: fused conv + LSTM cell step (training variant, also writes gates)",
+                          "convgemm_kernel<__half, 0>"),
+            "dgradT_fused_kernel": ("dgradT_fused_kernel: data gradient + fused gate gradient of the next chain step",
+                                    "dgradT_fused_kernel"),
+            "wgrad[halo rows]": ("wgrad_kernel (halo rows): weight gradient", "wgrad_kernel"),
+            "wgrad_gate_kernel": ("wgrad_kernel + gate-gradient worker warps", "wgrad_kernel"),
+            "dgradT_kernel": ("dgradT_kernel: data gradient", "dgradT_kernel"),
+        }
+        in_situ = []
+        for key, (label, ncu_name) in tensor_kernels.items():
+            if key not in tr:
+                continue
+            n, tot_ms, avg_us = tr[key]
+            ach = fl / (avg_us * 1e-6) / 1e12
+            traffic, tsrc = ncu_traffic(ncu_name)
+            in_situ.append({"kernel": label, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
+                            "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
+                            "traffic_source": tsrc, "launch_ms": avg_us * 1e-3, "launches_per_step": n // 2,
+                            "share_of_step_ms": tot_ms / 2, "flops_per_launch": fl,
+                            "peak_source": peaks["source"] + " sustained: kernel timed inside the training step",
+                            "timing": "CUDA event after every launch of 2 training steps on the launching stream "
+                                      "(clstm_trace_enable), taken right after the timed region"})
+        if "gate_grad_kernel" in tr:
+            n, tot_ms, avg_us = tr["gate_grad_kernel"]
+            in_situ.append({"kernel": "gate_grad_kernel (pointwise gate gradient, standalone launches)", "bound": "hbm",
+                            "achieved": gg_bytes / (avg_us * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": gg_bytes / (avg_us * 1e-6) / 1e9 / peaks["hbm"], "launch_ms": avg_us * 1e-3,
+                            "launches_per_step": n // 2, "share_of_step_ms": tot_ms / 2})
+        in_situ.sort(key=lambda d: -d.get("share_of_step_ms", 0.0))
+        if in_situ:
+            roof = in_situ[0]  # the kernel with the largest share of the step
+            extra["kernels_in_step"] = in_situ[1:]
+        extra["trace_top"] = {k: {"n_per_step": v[0] // 2, "ms_per_step": v[1] / 2, "avg_us": v[2]}
+                              for k, v in sorted(tr.items(), key=lambda kv: -kv[1][1])[:10]}
+
+        # (2) ISOLATED: each kernel launched alone, back to back, through the C-ABI measurement hook -> burst peak.
+        # (20 back-to-back launches of one tensor-bound kernel draw more power than the mixed step: lower clocks.)
         plan = [p for p in model.model._plans.values() if p.training][0]
 
         def time_kernel(kind, cell, step, reps=20):
@@ -291,57 +541,44 @@ def run_ours(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b_) / reps
 
-        fl = cell_step_flops(B, hid, hid, HW, HW)  # decoder_2: K = (64 + 64) * 9
-        k_ms = time_kernel("cell_fwd", 3, 5)
-        ach = fl / k_ms / 1e9
-        roof = {"kernel": "convgemm_kernel<EPI_LSTM> (fused cell step, training variant: also writes gates)",
-                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_burst"], "traffic": 1.43e9, "launch_ms": k_ms,
-                "flops_per_launch": fl, "peak_source": peaks["source"] + " burst, kernel timed alone",
-                "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r1_v2_ncu_full_summary.csv)"}
-        others = []
-        for kind, name in (("dgrad", "dgradT_kernel (data gradient)"), ("wgrad", "wgrad_kernel (weight gradient)")):
-            ms = time_kernel(kind, 3, 5)
-            others.append({"kernel": name, "bound": "tensor", "achieved": fl / ms / 1e9, "peak": peaks["bf16_burst"],
-                           "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peaks["bf16_burst"], "launch_ms": ms})
-        npix = B * HW * HW
-        gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
-        ms = time_kernel("gate_grad", 3, 5)
-        others.append({"kernel": "gate_grad_kernel (pointwise gate gradient)", "bound": "hbm",
-                       "achieved": gg_bytes / ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
-                       "frac": gg_bytes / ms / 1e6 / peaks["hbm"], "launch_ms": ms})
-        # default backward schedule: the gate gradient of the next chain step runs in the dgrad epilogue, so the
-        # launch does both the GEMM flops and the pointwise pass's bytes; reported against the tensor peak
-        ms = time_kernel("dgrad_fused", 3, 5)
-        fused = {"kernel": "dgradT_fused_kernel (data gradient + fused gate gradient of the cell below)",
-                 "bound": "tensor", "achieved": fl / ms / 1e9, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                 "frac": fl / ms / 1e9 / peaks["bf16_burst"], "traffic": 3.31e9, "launch_ms": ms,
-                 "flops_per_launch": fl, "fused_hbm_GBps": gg_bytes / ms / 1e6,
-                 "peak_source": peaks["source"] + " burst, kernel timed alone",
-                 "traffic_source": "ncu --set full dram__bytes_read+write per launch "
-                                   "(profiles/r1_v2_ncu_full_summary.csv); algorithmic 3.24 GB"}
-        # `roofline` is the kernel with the largest share of the step: 71 fused dgrad launches vs 72 cell steps
-        roof["launches_per_step"] = 2 * (t_in + t_out)
-        fused["launches_per_step"] = 2 * (t_in + t_out) - 1
-        if fused["launch_ms"] * fused["launches_per_step"] > roof["launch_ms"] * roof["launches_per_step"]:
-            roof, fused = fused, roof
-        others.append(fused)
-        extra["kernels"] = others
-        flops_step = 3 * algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW)
+        iso = []
+        for kind, name in (("cell_fwd", "fused cell step"), ("dgrad_fused", "dgradT + fused gate gradient"),
+                           ("dgrad", "dgradT alone"), ("wgrad", "wgrad")):
+            try:
+                ms = time_kernel(kind, 3, 5)
+            except Exception as e:
+                iso.append({"kernel": name, "error": str(e)[:120]})
+                continue
+            iso.append({"kernel": name, "bound": "tensor", "achieved": fl / ms / 1e9, "peak": peaks["bf16_burst"],
+                        "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peaks["bf16_burst"], "launch_ms": ms})
+        extra["kernels_isolated"] = {"how": "20 back-to-back launches of one kernel on the plan's tensors (timing only: "
+                                            "backward kinds re-run on whatever the last backward left), burst peak",
+                                     "rows": iso}
+        flops_step = 3 * algorithmic_flops_fwd(B * n_micro, t_in, t_out, C, hid, Co, HW, HW)
         extra["step_tflops"] = flops_step * world / ms_step / 1e9
         extra["step_frac_of_sustained_peak"] = flops_step / ms_step / 1e9 / peaks["bf16_sustained"]
-        threads = os.cpu_count() or 1
-        if not args.no_cpu:
-            r = cpu_reference_sample(1, 1, threads)
-            cpu = {"value": r["value"], "unit": "frames/s", "cores": threads, "kind": "port", "sample": r["sample"]}
+        st = model.model.check_gradients()
+        if st:
+            extra["grad_range"] = {k: st[k] for k in ("scale", "amax_dlogit", "amax_dz_scaled", "headroom_log2")}
+
+    # other BASELINE configs (rank 0, single GPU, on request off): parity for them lives in tests/; here only numbers
+    if rank == 0 and world == 1 and not args.no_extras:
+        model.model.release_plans()
+        del model, bucket, opt, x_dev, y_dev
+        torch.cuda.empty_cache()
+        extra["other_configs"] = other_configs(ConvLSTM, ConvLSTMCell, dev, peaks)
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_subprocess()
 
     if rank == 0:
-        frames = world * B * (t_in + t_out)
+        frames = world * B * n_micro * (t_in + t_out)
         line = {
             "metric": METRIC, "value": frames / ms_step * 1e3, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, args.global_batch),
             "e2e": {"value": frames / ms_e2e * 1e3, "unit": "frames/s",
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -352,6 +589,83 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_configs(ConvLSTM, ConvLSTMCell, dev, peaks):
+    """BASELINE configs[0], [3] and a subset of the configs[4] cell sweep, device-timed (CUDA events, 3 warm-up)."""
+    out = {}
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def rollout(name, B, t_in, t_out, hid, hw, n_layers, reps):
+        torch.manual_seed(0)
+        net = ConvLSTM(12, hid, 12, n_layers=n_layers).to(dev)
+        x = torch.randn(B, t_in, 12, hw, hw, device=dev)
+        tgt = torch.rand(B, t_out, 12, hw, hw, device=dev)
+
+        def train():
+            net.zero_grad(set_to_none=True)
+            torch.nn.functional.mse_loss(net(x, t_out).permute(0, 2, 1, 3, 4), tgt).backward()
+
+        def infer():
+            with torch.no_grad():
+                net(x, t_out)
+
+        try:
+            ms_t, ms_i = timeit(train, reps), timeit(infer, reps)
+            fl = algorithmic_flops_fwd(B, t_in, t_out, 12, hid, 12, hw, hw, n_layers=n_layers)
+            out[name] = {"fwd_bwd_ms": ms_t, "fwd_bwd_frames_per_s": B * (t_in + t_out) / ms_t * 1e3,
+                         "fwd_bwd_tflops": 3 * fl / ms_t / 1e9, "fwd_ms": ms_i,
+                         "fwd_frames_per_s": B * (t_in + t_out) / ms_i * 1e3, "fwd_tflops": fl / ms_i / 1e9}
+        except Exception as e:
+            out[name] = {"error": str(e)[:200]}
+        net.release_plans()
+        del net, x, tgt
+        torch.cuda.empty_cache()
+
+    rollout("configs[0]: 1-layer hid 32, 12ch 64x64, 4 in / 4 out, batch 2", 2, 4, 4, 32, 64, 1, 20)
+    rollout("configs[0] on the reference's 2+2 architecture", 2, 4, 4, 32, 64, 2, 20)
+    rollout("configs[3]: 3-layer hid 128, 12ch 512x512, 12 in / 12 out, batch 1", 1, 12, 12, 128, 512, 3, 3)
+    cells = []
+    for k, hid, px in ((3, 64, 128), (3, 64, 256), (3, 64, 512), (5, 64, 256), (3, 128, 256), (3, 256, 256), (5, 128, 128)):
+        try:
+            torch.manual_seed(0)
+            cell = ConvLSTMCell(hid, hid, (k, k), True).to(dev)
+            x = torch.randn(1, hid, px, px, device=dev)
+            h = torch.randn(1, hid, px, px, device=dev) * 0.5
+            c = torch.randn(1, hid, px, px, device=dev)
+
+            def fwd():
+                with torch.no_grad():
+                    cell(x, [h, c])
+
+            hg, cg = h.clone().requires_grad_(True), c.clone().requires_grad_(True)
+
+            def fwd_bwd():
+                cell.zero_grad(set_to_none=True)
+                hn, cn = cell(x, [hg, cg])
+                (hn.sum() + cn.sum()).backward()
+
+            fl = cell_step_flops(1, hid, hid, px, px, k)
+            ms_f, ms_fb = timeit(fwd, 10), timeit(fwd_bwd, 5)
+            cells.append({"kernel": f"{k}x{k}", "hidden": hid, "px": px, "fwd_ms": ms_f, "fwd_tflops": fl / ms_f / 1e9,
+                          "fwd_bwd_ms": ms_fb, "fwd_bwd_tflops": 3 * fl / ms_fb / 1e9})
+            del cell, x, h, c, hg, cg
+            torch.cuda.empty_cache()
+        except Exception as e:
+            cells.append({"kernel": f"{k}x{k}", "hidden": hid, "px": px, "error": str(e)[:200]})
+    out["configs[4] subset: ConvLSTMCell through the drop-in NCHW fp32 module API (B=1, Cin_x = hidden)"] = cells
+    return out
 
 
 _REAL_STDOUT = None
@@ -378,12 +692,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (configs[0], [3], [4])")
+    ap.add_argument("--check", action="store_true", help="multi-GPU gradient-equivalence check instead of the benchmark")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fixed global batch (multiple of 16 * gpus), micro-batches of 16 per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager-gpu":
+        run_eager_gpu(args)
+    elif args.check:
+        run_check(args)
     else:
         run_ours(args)
 

@@ -430,7 +430,7 @@ template <typename E, int EPI>
 int launch_convgemm(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                     ConvGemmParams p, const Geo& g, long long images, cudaStream_t st,
                     const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr,
-                    const CUtensorMap* x3 = nullptr) {
+                    const CUtensorMap* x3 = nullptr, const char* name = "convgemm_kernel") {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
@@ -461,7 +461,7 @@ int launch_convgemm(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1,
   const int grid = total < dev.sms ? total : dev.sms;
   convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0 ? *x0 : b, x1 ? *x1 : b, x2 ? *x2 : b,
                                                             x3 ? *x3 : (x0 ? *x0 : b), p);
-  return after_launch("convgemm_kernel");
+  return after_launch(name);
 }
 
 // Transposed dgrad (dgradT.cuh): channels as M, 256 pixels as N.
@@ -581,7 +581,8 @@ int launch_head_rows(const Ctx& cx, const CUtensorMap& h128, const CUtensorMap& 
 
 template <typename E>
 int launch_wgrad(const Ctx& cx, const CUtensorMap& a, const CUtensorMap& b0, const CUtensorMap& b1,
-                 WgradParams p, const Geo& g, long long images, cudaStream_t st, const WgGateWork* gate = nullptr) {
+                 WgradParams p, const Geo& g, long long images, cudaStream_t st, const WgGateWork* gate = nullptr,
+                 const char* name = "wgrad_kernel") {
   const DeviceInfo& dev = cx.dev;
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW2, p.BH = g.BH2, p.tiles_w = g.tiles_w2, p.tiles_h = g.tiles_h2;
@@ -612,7 +613,7 @@ int launch_wgrad(const Ctx& cx, const CUtensorMap& a, const CUtensorMap& b0, con
   WgGateWork none;
   memset(&none, 0, sizeof(none));
   wgrad_kernel<E, 0><<<grid, kWgThreads, smem, st>>>(a, b0, b1, p, none);
-  return after_launch("wgrad_kernel");
+  return after_launch(name);
 }
 
 // Row-tiled im2col when its shared-memory tile fits, else the generic gather kernels.
@@ -629,7 +630,7 @@ int launch_row_im2col(const float* s0, const float* s1, E* out, int B, int T, in
   }
   row_im2col_kernel<E, MODE><<<nt * B * H, 256, smem, st>>>(s0, s1, out, B, T, C, H, W, kh, kw, KP, t0, scale_ptr);
   *used = true;
-  return after_launch("row_im2col_kernel");
+  return after_launch(MODE == 1 ? "head_dlogit_im2col" : "x_im2col");
 }
 
 // --------------------------------------------------------------------------- cell building blocks
@@ -674,9 +675,11 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
     p.hnext_boff = sn * ctx.geo.B;
     p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
     return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
-                                        &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16);
+                                        &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16, nullptr,
+                                        g.in_col ? "cell_step[x im2col]" : "cell_step");
   }
-  return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st);
+  return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, nullptr, nullptr,
+                                      nullptr, nullptr, "cell_step[direct stores]");
 }
 
 // Backward of one cell step, three launches: fused gate gradient -> dgrad (dx | dh_prev) -> wgrad
@@ -716,7 +719,8 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
     if (used) return 0;
   }
   return launch_convgemm<E, EPI_STORE>(ctx, ctx.m_dz128b[buf], ctx.m_dz128b[buf], cs.m_wd, p, ctx.geo, ctx.geo.B, st,
-                                       cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16);
+                                       cs.with_x ? &cs.m_dx16 : &cs.m_dh16, &cs.m_dh16, &cs.m_dh16, nullptr,
+                                       "dgrad[pixel-major]");
 }
 
 // slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
@@ -784,9 +788,10 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
   if (!g.in_col && g.kh == 3 && g.kw == 3 && g.CIP == 64 && ctx.HP == 64 && geo.BW2 == 64 && geo.BH2 == 1 &&
       cs.wg_group == 6 && cs.wg_total == 18 && in.map66 != nullptr && ctx.knobs.wg_halo) {
     p.halo = 1;
-    return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st, gate);
+    return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map66, cs.m_h66, p, geo, geo.B, st, gate, "wgrad[halo rows]");
   }
-  return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st, gate);
+  return launch_wgrad<E>(ctx, ctx.m_dz64b[buf], *in.map64, cs.m_h64, p, geo, geo.B, st, gate,
+                         g.in_col ? "wgrad[x im2col]" : "wgrad[boxes]");
 }
 
 template <typename E>
@@ -1013,7 +1018,8 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
         RC_TRY((launch_head_rows<E>(ctx, last.m_h128, p->m_wz, rp, geo, st, &used)));
         if (used) continue;
       }
-      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx, last.m_h128, last.m_h128, p->m_wh, hp, geo, images, st)));
+      RC_TRY((launch_convgemm<E, EPI_HEAD>(ctx, last.m_h128, last.m_h128, p->m_wh, hp, geo, images, st, nullptr, nullptr,
+                                           nullptr, nullptr, "head_conv[implicit GEMM]")));
     }
   }
   p->forward_done = true;
@@ -1107,7 +1113,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       hp.split_col = HP, hp.ld0 = HP, hp.ld1 = HP;
       hp.out_scale = 1.f;
       RC_TRY((launch_convgemm<E, EPI_STORE>(ctx, p->m_G128, p->m_G128, p->m_whd, hp, geo, c.batch, st,
-                                            &p->m_dstack16, &p->m_dstack16, &p->m_dstack16)));
+                                            &p->m_dstack16, &p->m_dstack16, &p->m_dstack16, nullptr, "head_dgrad")));
     }
     {
       WgradParams wp;
@@ -1120,7 +1126,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       wp.splits = p->head_splits;
       wp.partial = p->hpart;
       wp.accumulate = (t != c.t_out - 1);
-      RC_TRY((launch_wgrad<E>(ctx, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st)));
+      RC_TRY((launch_wgrad<E>(ctx, p->m_G64, last.m_h64, last.m_h64, wp, geo, c.batch, st, nullptr, "head_wgrad")));
     }
     return 0;
   };
