@@ -225,28 +225,64 @@ def workload_config(n, global_batch=None):
 
 # ------------------------------------------------------------------------------------------ informational GPU-eager arm
 def run_eager_gpu(args):
-    """SURVEY.md §0 names PyTorch eager (cuDNN conv + ATen pointwise) on the same B200 as the bar: the oracle's op
-    sequence (= the reference's) on the GPU with torch's defaults for convolutions (cudnn.allow_tf32 = True), largest
-    batch that fits next to autograd's saved activations.  Informational; not part of the driver's contract."""
-    from oracle import convlstm_oracle as O
+    """SURVEY.md §0 names PyTorch eager (cuDNN conv + ATen pointwise) on the same B200 as the bar to beat: the
+    reference's op sequence (layers/ConvLSTM.py:42-57 inside the loops of conv_lstm.py:171-203) written with plain
+    torch modules on the GPU, torch's defaults for convolutions (cudnn.allow_tf32 = True), autograd backward, fused
+    Adam, largest batch of {16, 8, 4, 2, 1} that fits next to autograd's saved activations.  Informational; not part of
+    the driver's contract and not the parity oracle."""
+    import torch.nn as nn
+
+    class Cell(nn.Module):
+        def __init__(self, cin, hid):
+            super().__init__()
+            self.hid = hid
+            self.conv = nn.Conv2d(cin + hid, 4 * hid, 3, padding=1, bias=True)
+
+        def forward(self, x, h, c):
+            i, f, o, g = torch.split(self.conv(torch.cat([x, h], dim=1)), self.hid, dim=1)
+            i, f, o, g = torch.sigmoid(i), torch.sigmoid(f), torch.sigmoid(o), torch.tanh(g)
+            c = f * c + i * g
+            return o * torch.tanh(c), c
+
+    class Net(nn.Module):
+        def __init__(self, cin, hid, cout):
+            super().__init__()
+            self.hid = hid
+            self.cells = nn.ModuleList([Cell(cin, hid), Cell(hid, hid), Cell(hid, hid), Cell(hid, hid)])
+            self.head = nn.Conv3d(hid, cout, (1, 3, 3), padding=(0, 1, 1))
+
+        def forward(self, x, t_out):
+            B, T, _, H, W = x.shape
+            hs = [torch.zeros(B, self.hid, H, W, device=x.device) for _ in range(4)]
+            cs = [torch.zeros(B, self.hid, H, W, device=x.device) for _ in range(4)]
+            for t in range(T):
+                hs[0], cs[0] = self.cells[0](x[:, t], hs[0], cs[0])
+                hs[1], cs[1] = self.cells[1](hs[0], hs[1], cs[1])
+            vec, outs = hs[1], []
+            for _ in range(t_out):
+                hs[2], cs[2] = self.cells[2](vec, hs[2], cs[2])
+                hs[3], cs[3] = self.cells[3](hs[2], hs[3], cs[3])
+                vec = hs[3]
+                outs.append(vec)
+            return torch.sigmoid(self.head(torch.stack(outs, 1).permute(0, 2, 1, 3, 4)))
 
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
     t_in, t_out = CFG["t_in"], CFG["t_out"]
-    res = None
+    res, tried = None, []
     for B in (16, 8, 4, 2, 1):
+        net = x = tgt = opt = None
         try:
-            g = torch.Generator().manual_seed(1234)
-            p = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params(CFG["channels"], CFG["hidden"], CFG["out_channels"], seed=0).items()}
-            x = torch.randn(B, t_in, CFG["channels"], CFG["hw"], CFG["hw"], generator=g).to(dev)
-            tgt = torch.rand(B, t_out, CFG["out_channels"], CFG["hw"], CFG["hw"], generator=g).to(dev)
-            opt = torch.optim.Adam(list(p.values()), lr=1e-4, fused=True)
+            torch.manual_seed(0)
+            net = Net(CFG["channels"], CFG["hidden"], CFG["out_channels"]).to(dev)
+            x = torch.randn(B, t_in, CFG["channels"], CFG["hw"], CFG["hw"], device=dev)
+            tgt = torch.rand(B, t_out, CFG["out_channels"], CFG["hw"], CFG["hw"], device=dev)
+            opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
 
             def step():
                 opt.zero_grad(set_to_none=True)
-                y, _ = O.rollout_forward(x, p, t_out)
-                loss = torch.nn.functional.mse_loss(y.permute(0, 2, 1, 3, 4), tgt)
+                loss = torch.nn.functional.mse_loss(net(x, t_out).permute(0, 2, 1, 3, 4), tgt)
                 loss.backward()
                 opt.step()
 
@@ -262,20 +298,21 @@ def run_eager_gpu(args):
             ms = e0.elapsed_time(e1) / args.steps
             with torch.no_grad():
                 for _ in range(2):
-                    O.rollout_forward(x, p, t_out)
+                    net(x, t_out)
                 torch.cuda.synchronize()
                 e0.record()
                 for _ in range(args.steps):
-                    O.rollout_forward(x, p, t_out)
+                    net(x, t_out)
                 e1.record()
                 torch.cuda.synchronize()
             ms_inf = e0.elapsed_time(e1) / args.steps
             res = dict(batch=B, ms_per_step=ms, frames_per_s=B * (t_in + t_out) / ms * 1e3,
                        inference_ms=ms_inf, inference_frames_per_s=B * (t_in + t_out) / ms_inf * 1e3,
-                       peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
+                       peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9, batches_that_did_not_fit=tried)
             break
         except torch.OutOfMemoryError:
-            del p, x, tgt
+            tried.append(B)
+            del net, x, tgt, opt
             torch.cuda.empty_cache()
     emit({"impl": "eager-gpu", "metric": METRIC, "value": res["frames_per_s"] if res else None, "unit": "frames/s",
           "n_gpus": 1, "dtype": "tf32 conv (cudnn.allow_tf32) / fp32 pointwise", "data": "synthetic",

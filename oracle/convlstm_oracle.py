@@ -205,7 +205,7 @@ def rollout_forward(
     names = cell_names(n_layers)
     hid = params[f"{names[0]}.conv.bias"].numel() // 4
     ncell = 2 * n_layers
-    zeros = lambda: torch.zeros(B, hid, H, W, dtype=torch.float32)
+    zeros = lambda: torch.zeros(B, hid, H, W, dtype=torch.float32, device=x.device)  # layers/ConvLSTM.py:59-64
     h = [zeros() for _ in range(ncell)]  # :218-221
     c = [zeros() for _ in range(ncell)]
     sv = Saved(x=x, n_layers=n_layers, t_in=T_in, t_out=forecast_steps)

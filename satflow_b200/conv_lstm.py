@@ -152,7 +152,7 @@ class ConvLSTM(nn.Module):
                     plan2 = None
             if plan2 is not None and not plan2.pending_backward:
                 return plan2
-            return plan if plan2 is None or plan.generation <= plan2.generation else plan2
+            return plan if plan2 is None or plan.last_use <= plan2.last_use else plan2  # sacrifice the oldest graph
         if plan is None:
             # bounded cache (a training plan pins tens of GB); plans with an outstanding backward are never evicted
             evictable = [k for k, pl in self._plans.items() if not pl.pending_backward]

@@ -22,6 +22,7 @@
 #include "dgradT.cuh"
 #include "head_rows.cuh"
 #include "pointwise.cuh"
+#include "rollout_persist.cuh"
 #include "wgrad.cuh"
 
 using namespace clstm;
@@ -106,6 +107,7 @@ struct Knobs {
   int wg_gate = 0;          // CLSTM_WG_GATE: gate gradient on worker warps inside wgrad (1: plain, 2: setmaxnreg)
   int wg_group = kWgMaxGroupBlocks;  // CLSTM_WG_GROUP: column blocks per wgrad CTA
   int overlap = 0;          // CLSTM_OVERLAP: wgrad on a side stream
+  int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
   void read() {
     stages = env_int("CLSTM_STAGES", stages);
     rotate = env_int("CLSTM_ROTATE", rotate);
@@ -122,6 +124,7 @@ struct Knobs {
     wg_group = env_int("CLSTM_WG_GROUP", wg_group);
     if (wg_group < 1 || wg_group > kWgMaxGroupBlocks) wg_group = kWgMaxGroupBlocks;
     overlap = env_int("CLSTM_OVERLAP", overlap);
+    persist = env_int("CLSTM_PERSIST", persist);
   }
 };
 
@@ -362,10 +365,12 @@ void wgrad_shape(const DeviceInfo& dev, int max_group, int total_blocks, int n_b
 }
 
 // Fills the derived fields of a cell.  in_col: the input is an im2col'd tensor (rollout encoder_1).
-void init_cell(CellState* cs, const Ctx& ctx, int cin, int hid, int kh, int kw, int in_col, int with_x, int T) {
+void init_cell(CellState* cs, const Ctx& ctx, int cin, int hid, int kh, int kw, int in_col, int with_x, int T,
+               int in_scaled) {
   CellGeom& g = cs->g;
   g.cin = cin, g.hid = hid, g.HP = ctx.HP, g.kh = kh, g.kw = kw, g.in_col = in_col;
   g.CIP = round_up(cin, 64);
+  g.in_scaled = in_scaled;
   g.KIN = in_col ? round_up(kh * kw * cin, 64) : kh * kw * g.CIP;
   cs->T = T;
   cs->Kf = g.KIN + kh * kw * g.HP;
@@ -863,6 +868,13 @@ struct clstm_plan {
   int hb_chunks = 1;          // pieces per (b, c) run in head_grad_stats_kernel
   int head_splits = 0, head_group = 0, n_tile_hd = 0;
   CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16, m_wz;
+  // persistent forward chain (rollout_persist.cuh): device copies of the tensor maps and of the step table
+  bool persist_ok = false;
+  int persist_stages = 0;
+  void* pmaps = nullptr;
+  void* psteps = nullptr;
+  unsigned int* pcounter = nullptr;
+  PersistParams pparams;
 };
 
 namespace {
@@ -881,6 +893,9 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
   p->wh = cv.take<void>(static_cast<size_t>(p->NT) * 9 * HP * 2);
   p->bias_h = cv.take<float>(static_cast<size_t>(p->NT) * 4);
   p->wz = (c.out_channels <= 16) ? cv.take<void>(static_cast<size_t>(HP / 64) * kHrN * 64 * 2) : nullptr;
+  p->pmaps = cv.take<void>(static_cast<size_t>(kPersistMaxMaps) * sizeof(CUtensorMap));
+  p->psteps = cv.take<void>(static_cast<size_t>(p->L) * (c.t_in + c.t_out) * sizeof(PersistStep));
+  p->pcounter = reinterpret_cast<unsigned int*>(cv.take<float>(64));
   if (c.training) {
     ctx.dzb[0] = cv.take<void>(npix * 4 * HP * 2);
     ctx.dzb[1] = cv.take<void>(npix * 4 * HP * 2);
@@ -918,6 +933,105 @@ InputRef plan_input(clstm_plan* p, int k, int t) {
     in.map128 = &src.m_h128, in.map64 = &src.m_h64, in.map66 = &src.m_h66, in.b_off = hslot(src, t + 1) * B;
   }
   return in;
+}
+
+// Persistent forward chain (rollout_persist.cuh): eligible when every (pixel tile, 64-channel slice) gets its own CTA
+// and the cell states fit in TMEM next to the accumulator.  Builds the device-side tensor-map table and step table.
+int persist_setup(clstm_plan* p, cudaStream_t st) {
+  const clstm_config_t& c = p->cfg;
+  Ctx& ctx = p->ctx;
+  const Geo& geo = ctx.geo;
+  p->persist_ok = false;
+  const int n_tiles = ctx.HP / 64;
+  const long long tiles = static_cast<long long>(geo.B) * geo.tiles_w * geo.tiles_h * n_tiles;
+  if (!ctx.knobs.persist || !ctx.knobs.staged || p->ncell > kPersistMaxCells || tiles > ctx.dev.sms) return 0;
+  if (1 + 5 * p->ncell > kPersistMaxMaps) return 0;
+  for (int k = 0; k < p->ncell; ++k)
+    if (p->cells[k].Kf / 64 > kKtabMax) return 0;
+  int stages = (ctx.dev.smem_optin - static_cast<int>(persist_smem_bytes(0, p->ncell))) / (kABytes + 256 * 128);
+  if (stages > ctx.knobs.stages) stages = ctx.knobs.stages;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return 0;
+  p->persist_stages = stages;
+  std::vector<CUtensorMap> maps(kPersistMaxMaps);
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  maps[0] = p->m_xcol128;
+  PersistParams& pp = p->pparams;
+  memset(&pp, 0, sizeof(pp));
+  for (int k = 0; k < p->ncell; ++k) {
+    const CellState& cs = p->cells[k];
+    const int base = 1 + 5 * k;
+    maps[base + 0] = cs.m_h128, maps[base + 1] = cs.m_wp, maps[base + 2] = cs.m_c16, maps[base + 3] = cs.m_h16;
+    maps[base + 4] = c.training ? cs.m_g16 : cs.m_h16;
+    PersistCell& pc = pp.cells[k];
+    const CellGeom& g = cs.g;
+    pc.seg[0] = g.in_col ? ConvSeg{g.KIN / 64, 1, 1, 0} : ConvSeg{g.CIP / 64, g.kh, g.kw, 0};
+    pc.seg[1] = ConvSeg{ctx.HP / 64, g.kh, g.kw, 0};
+    pc.kblocks = cs.Kf / 64;
+    pc.map_a1 = base + 0, pc.map_b = base + 1, pc.map_xc = base + 2, pc.map_xh = base + 3, pc.map_xg = base + 4;
+    pc.bias = cs.bias_p;
+  }
+  std::vector<PersistStep> steps;
+  const int L = p->L, B = c.batch;
+  auto add = [&](int k, int t) {
+    const CellState& cs = p->cells[k];
+    PersistStep s;
+    memset(&s, 0, sizeof(s));
+    s.cell = k;
+    if (k == 0) {
+      s.map_a0 = 0, s.a0_boff = t * B;  // x[:, t] (conv_lstm.py:177)
+    } else if (k == L) {
+      const int src = (t == 0) ? L - 1 : p->ncell - 1;  // encoder_vector (:185) / last decoder h (:195)
+      s.map_a0 = 1 + 5 * src;
+      s.a0_boff = ((t == 0) ? hslot(p->cells[src], c.t_in) : hslot(p->cells[src], t)) * B;
+    } else {
+      s.map_a0 = 1 + 5 * (k - 1);
+      s.a0_boff = hslot(p->cells[k - 1], t + 1) * B;
+    }
+    s.a1_boff = hslot(cs, t) * B;
+    s.hnext_boff = hslot(cs, t + 1) * B;
+    s.cnext_boff = cslot(cs, t + 1) * B;
+    s.gates_boff = t * B;
+    s.first = (t == 0) ? 1 : 0;
+    s.store_c = (c.training || t == cs.T - 1) ? 1 : 0;
+    steps.push_back(s);
+  };
+  for (int t = 0; t < c.t_in; ++t)
+    for (int l = 0; l < L; ++l) add(l, t);
+  for (int t = 0; t < c.t_out; ++t)
+    for (int l = 0; l < L; ++l) add(L + l, t);
+  CU_TRY(cudaMemcpyAsync(p->pmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(p->psteps, steps.data(), steps.size() * sizeof(PersistStep), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));  // the host vectors die with this scope
+  pp.B = geo.B, pp.H = geo.H, pp.W = geo.W, pp.BW = geo.BW, pp.BH = geo.BH, pp.tiles_w = geo.tiles_w, pp.tiles_h = geo.tiles_h;
+  pp.num_m_tiles = geo.B * geo.tiles_w * geo.tiles_h;
+  pp.n_tiles = n_tiles;
+  pp.ldc = ctx.HP;
+  pp.stages = stages, pp.nsteps = static_cast<int>(steps.size()), pp.ncell = p->ncell, pp.training = c.training ? 1 : 0;
+  pp.rotate = ctx.knobs.rotate ? 1 : 0;
+  pp.maps = static_cast<const CUtensorMap*>(p->pmaps);
+  pp.steps = static_cast<const PersistStep*>(p->psteps);
+  pp.counter = p->pcounter;
+  p->persist_ok = true;
+  return 0;
+}
+
+template <typename E>
+int launch_persist(clstm_plan* p, cudaStream_t st) {
+  const size_t smem = persist_smem_bytes(p->persist_stages, p->ncell);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(rollout_persist_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                p->ctx.dev.smem_optin));
+    attr_set = true;
+  }
+  CU_TRY(cudaMemsetAsync(p->pcounter, 0, 4, st));
+  void* args[] = {&p->pparams};
+  const int grid = p->pparams.num_m_tiles * p->pparams.n_tiles;
+  // cooperative launch: every CTA must be resident, each one waits for the h tiles of all others between steps
+  CU_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rollout_persist_kernel<E>), dim3(grid), dim3(kGemmThreads),
+                                     args, smem, st));
+  return after_launch("rollout_persist_kernel");
 }
 
 template <typename E>
@@ -980,10 +1094,14 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
     return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st, cslot(cs, t),
                                 cslot(cs, t + 1), t);
   };
-  for (int t = 0; t < c.t_in; ++t)  // conv_lstm.py:176-183
-    for (int l = 0; l < L; ++l) RC_TRY(step(l, t));
-  for (int t = 0; t < c.t_out; ++t)  // conv_lstm.py:188-196
-    for (int l = 0; l < L; ++l) RC_TRY(step(L + l, t));
+  if (p->persist_ok) {
+    RC_TRY(launch_persist<E>(p, st));  // the whole chain below in one launch, c resident in TMEM
+  } else {
+    for (int t = 0; t < c.t_in; ++t)  // conv_lstm.py:176-183
+      for (int l = 0; l < L; ++l) RC_TRY(step(l, t));
+    for (int t = 0; t < c.t_out; ++t)  // conv_lstm.py:188-196
+      for (int l = 0; l < L; ++l) RC_TRY(step(L + l, t));
+  }
   // head: Conv3d(1,3,3) + Sigmoid over the last-decoder h of every output step (conv_lstm.py:198-201).  The
   // h slots are permuted in memory, so the head runs once per output frame (B images each) and writes frame t
   // of y directly — the reference's stack / permute copies (:198-199) never exist.
@@ -1267,7 +1385,8 @@ int plan_read_state(clstm_plan* p, int cell, int step, float* h_out, float* c_ou
   const int HP = p->ctx.HP;
   if (h_out) {
     const E* src = static_cast<const E*>(cs.h) + static_cast<size_t>(hslot(cs, step)) * npix * HP;
-    unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(src, h_out, c.batch, c.hidden, c.height, c.width, HP, nullptr, 0);
+    unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(src, h_out, c.batch, c.hidden, c.height, c.width, HP, nullptr, 0,
+                                                       kHScaleInv);
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   if (c_out) {
@@ -1326,10 +1445,10 @@ int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, con
   const size_t plane = static_cast<size_t>(geo.H) * geo.W;
   RC_TRY(pack_cell<E>(ctx, cs, weight, bias, st));
   pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xin), geo.B, p->cin, geo.H, geo.W, cs.g.CIP,
-                                                   p->cin * plane);
+                                                   p->cin * plane, 1.f);
   RC_TRY(after_launch("pack_nhwc_kernel"));
   pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(h_cur, static_cast<E*>(cs.h), geo.B, p->hid, geo.H, geo.W, HP,
-                                                   p->hid * plane);
+                                                   p->hid * plane, kHScale);
   RC_TRY(after_launch("pack_nhwc_kernel"));
   pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(c_cur, cs.c, geo.B, p->hid, geo.H, geo.W, HP, nullptr);
   RC_TRY(after_launch("pack_nhwc_f32_kernel"));
@@ -1338,7 +1457,7 @@ int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, con
   RC_TRY(cell_forward_step<E>(ctx, cs, in, 0, 1, cs.c, cs.c + npix * HP, cs.gates, st, 0, 1, 0));
   if (h_next) {
     unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(static_cast<const E*>(cs.h) + npix * HP, h_next, geo.B, p->hid,
-                                                       geo.H, geo.W, HP, nullptr, 0);
+                                                       geo.H, geo.W, HP, nullptr, 0, kHScaleInv);
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   if (c_next) {
@@ -1529,7 +1648,7 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
     CellState& cs = p->cells[k];
     const int T = (k < p->L) ? cfg->t_in : cfg->t_out;
     init_cell(&cs, ctx, k == 0 ? cfg->in_channels : cfg->hidden, cfg->hidden, cfg->kernel_h, cfg->kernel_w,
-              k == 0 ? 1 : 0, k == 0 ? 0 : 1, T);
+              k == 0 ? 1 : 0, k == 0 ? 0 : 1, T, k == 0 ? 0 : 1);  // every cell but the first reads another cell's h
     const bool full = cfg->training || k == p->ncell - 1;  // the head reads every last-decoder h
     cs.slots_h = full ? T + 1 : 2;
     cs.slots_c = cfg->training ? T + 1 : 2;
@@ -1611,6 +1730,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
     RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
+  RC_TRY(persist_setup(p, st));
   p->bound = true;
   p->weights_set = false;
   p->forward_done = false;
@@ -1770,7 +1890,7 @@ int clstm_cell_plan_create(int batch, int height, int width, int in_channels, in
   ctx.training = 1;
   ctx.grad_scale = 0.f;
   p->cin = in_channels, p->hid = hidden;
-  init_cell(&p->cs, ctx, in_channels, hidden, kernel_h, kernel_w, 0, 1, 1);
+  init_cell(&p->cs, ctx, in_channels, hidden, kernel_h, kernel_w, 0, 1, 1, 0);  // x is plain user data
   p->cs.slots_h = 2, p->cs.slots_c = 2;
   carve_cell_plan(p, nullptr, nullptr);
   *out = p;

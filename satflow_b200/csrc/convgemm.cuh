@@ -118,17 +118,18 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
         float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
-                                __uint_as_float(vo[e]) + bs[128 + j0 + e],
-                                __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+          lstm_gates_shared_rcp(fmaf(__uint_as_float(vi[e]), kHScaleInv, bs[0 + j0 + e]),
+                                fmaf(__uint_as_float(vf[e]), kHScaleInv, bs[64 + j0 + e]),
+                                fmaf(__uint_as_float(vo[e]), kHScaleInv, bs[128 + j0 + e]),
+                                fmaf(__uint_as_float(vg[e]), kHScaleInv, bs[192 + j0 + e]), gi[e], gf[e], go[e], gg[e]);
           cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
         }
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
           float ta, tb;
           tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
-          hn[e] = go[e] * ta;
-          hn[e + 1] = go[e + 1] * tb;
+          hn[e] = go[e] * ta * kHScale;  // stored scaled, see kHScale
+          hn[e + 1] = go[e + 1] * tb * kHScale;
         }
         float4* cdst = reinterpret_cast<float4*>(p.c_next + off);
 #pragma unroll
@@ -188,7 +189,7 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
         for (int e = 0; e < 16; ++e) {
           const int co = nt * p.n_tile + g * 16 + e;
           if (co < p.c_out)
-            ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(__uint_as_float(v[e]) + bias_s[co]);
+            ybase[static_cast<size_t>(co) * p.t_out * plane] = fast_sigmoid(fmaf(__uint_as_float(v[e]), kHScaleInv, bias_s[co]));
         }
       }
     }
@@ -446,17 +447,18 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             float cn[16], hn[16], gi[16], gf[16], go[16], gg[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              lstm_gates_shared_rcp(__uint_as_float(vi[e]) + bs[0 + j0 + e], __uint_as_float(vf[e]) + bs[64 + j0 + e],
-                                    __uint_as_float(vo[e]) + bs[128 + j0 + e],
-                                    __uint_as_float(vg[e]) + bs[192 + j0 + e], gi[e], gf[e], go[e], gg[e]);
+              lstm_gates_shared_rcp(fmaf(__uint_as_float(vi[e]), kHScaleInv, bs[0 + j0 + e]),
+                                    fmaf(__uint_as_float(vf[e]), kHScaleInv, bs[64 + j0 + e]),
+                                    fmaf(__uint_as_float(vo[e]), kHScaleInv, bs[128 + j0 + e]),
+                                    fmaf(__uint_as_float(vg[e]), kHScaleInv, bs[192 + j0 + e]), gi[e], gf[e], go[e], gg[e]);
               cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
             }
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
               float ta, tb;
               tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
-              hn[e] = go[e] * ta;
-              hn[e + 1] = go[e + 1] * tb;
+              hn[e] = go[e] * ta * kHScale;  // stored scaled, see kHScale
+              hn[e + 1] = go[e + 1] * tb * kHScale;
             }
             if (g2 == 1) {  // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
               tcgen05_fence_before();

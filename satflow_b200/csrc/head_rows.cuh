@@ -249,7 +249,7 @@ head_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
           float* yrow = ycol + static_cast<size_t>(R - 1) * p.W;
 #pragma unroll
           for (int o = 0; o < CO; ++o)
-            if (o < p.c_out) yrow[static_cast<size_t>(o) * p.t_out * plane] = fast_sigmoid(acc_a[o] + bias_r[o]);
+            if (o < p.c_out) yrow[static_cast<size_t>(o) * p.t_out * plane] = fast_sigmoid(fmaf(acc_a[o], kHScaleInv, bias_r[o]));
         }
 #pragma unroll
         for (int o = 0; o < CO; ++o) {

@@ -158,7 +158,7 @@ inline size_t row_im2col_smem_bytes(int C, int W, int kh, int kw, int KP) {
 // NCHW fp32 (optionally a (B,T,C,H,W) time slice) -> NHWC E with channel padding (zeros).
 template <typename E>
 __global__ void pack_nhwc_kernel(const float* __restrict__ src, E* __restrict__ dst, int B, int C, int H, int W,
-                                 int CP, size_t src_batch_stride) {
+                                 int CP, size_t src_batch_stride, float scale) {
   const int chunks = CP / 8;
   const size_t total = static_cast<size_t>(B) * H * W * chunks;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -171,7 +171,7 @@ __global__ void pack_nhwc_kernel(const float* __restrict__ src, E* __restrict__ 
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = ck * 8 + e;
-      v[e] = (c < C) ? __ldg(src + b * src_batch_stride + static_cast<size_t>(c) * H * W + hw) : 0.f;
+      v[e] = (c < C) ? scale * __ldg(src + b * src_batch_stride + static_cast<size_t>(c) * H * W + hw) : 0.f;
     }
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]),
                                                   Elem<E>::pack2(v[4], v[5]), Elem<E>::pack2(v[6], v[7]));
@@ -196,8 +196,8 @@ __global__ void pack_nhwc_f32_kernel(const float* __restrict__ src, float* __res
 // NHWC (E or fp32, channel stride CP) -> NCHW fp32 (C real channels).  scale applied.
 template <typename S>
 __global__ void unpack_nchw_kernel(const S* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
-                                   int CP, const float* __restrict__ scale_ptr, int accumulate) {
-  const float scale = scale_ptr ? *scale_ptr : 1.f;
+                                   int CP, const float* __restrict__ scale_ptr, int accumulate, float extra_scale = 1.f) {
+  const float scale = (scale_ptr ? *scale_ptr : 1.f) * extra_scale;
   const size_t total = static_cast<size_t>(B) * C * H * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -227,6 +227,7 @@ struct CellGeom {
                // 0: input segment is a conv over a CIP-channel NHWC tensor (k = tap*CIP + c, KIN = kh*kw*CIP)
   int CIP;     // input channels padded to a multiple of 64 (in_col == 0)
   int KIN;     // K extent of the input segment
+  int in_scaled;  // 1: the input tensor is a hidden state, i.e. stored times kHScale (ptx.cuh); 0: plain data (x)
 };
 
 // forward: Wp[row = nt*256 + gate*64 + jj][k], bias_p[row]
@@ -262,6 +263,8 @@ __global__ void pack_cell_weights_fwd_kernel(const float* __restrict__ w, const 
         if (c < g.hid) c_full = g.cin + c;
       }
       if (c_full >= 0) val = w[(static_cast<size_t>(n_ref) * ctot + c_full) * (g.kh * g.kw) + tap];
+      // the accumulator is z * kHScale (the h segment is stored scaled): a plain input gets the factor in its weights
+      if (k < g.KIN && !g.in_scaled) val *= kHScale;
       if (k == 0) bias_p[row] = bias ? bias[n_ref] : 0.f;
     } else if (k == 0) {
       bias_p[row] = 0.f;
@@ -659,14 +662,17 @@ __global__ void cell_wgrad_finalize_kernel(const float* __restrict__ partial, fl
     const int n_ref = static_cast<int>(i / (static_cast<size_t>(taps) * ctot));
     const int gate = n_ref / g.hid, j = n_ref % g.hid;
     size_t k;
-    if (c_full < g.cin)
+    float unscale = kHScaleInv;  // the wgrad operand of these columns was a hidden state stored times kHScale
+    if (c_full < g.cin) {
       k = g.in_col ? static_cast<size_t>(tap) * g.cin + c_full : static_cast<size_t>(tap) * g.CIP + c_full;
-    else
+      if (!g.in_scaled) unscale = 1.f;
+    } else {
       k = static_cast<size_t>(g.KIN) + static_cast<size_t>(tap) * g.HP + (c_full - g.cin);
+    }
     const float* src = partial + static_cast<size_t>(gate * g.HP + j) * K + k;
     float s = 0.f;
     for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
-    s *= scale;
+    s *= scale * unscale;
     dw[i] = accumulate ? dw[i] + s : s;
   }
 }
@@ -684,7 +690,7 @@ __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, fl
   const size_t split_stride = static_cast<size_t>(KG) * HP;
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
-  s *= scale;
+  s *= scale * kHScaleInv;  // the h-stack operand is stored times kHScale
   dw[i] = accumulate ? dw[i] + s : s;
 }
 

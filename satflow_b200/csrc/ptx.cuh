@@ -211,15 +211,54 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The reverse: thread i of the warp writes 16 consecutive 32-bit columns of lane (base_lane + i).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ grid-wide hand-off through global memory
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Orders accesses made through the async proxy (TMA) against generic-proxy accesses to global / shared memory.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ------------------------------------------------------------------ math / conversion
+// Range of the 16-bit hidden states.  |h| = |o * tanh(c)| < 1 always, but a freshly initialised or weight-clipped
+// network (CloudGAN: N(0, 0.02) / clamp 0.01, gan/common.py:44-64) drives h of the upper cells down to 1e-5, below
+// fp16's smallest normal (6.1e-5).  Every h tensor is therefore STORED as h * 2^12 (max 4096, smallest normal 1.5e-8);
+// a power-of-two factor is exact, so results in the old range are bit-identical.  Consumers undo it on fp32 values:
+// the conv / head accumulators are multiplied by 2^-12 (weights of an input segment that does not carry the factor —
+// x — are packed times 2^12 instead), weight-gradient columns of scaled operands are divided by it in the finalize.
+constexpr float kHScale = 4096.f;
+constexpr float kHScaleInv = 1.f / 4096.f;
+
 __device__ __forceinline__ float fast_sigmoid(float x) {
   // 1 / (1 + 2^(-x*log2e)): ex2.approx + rcp.approx (2 MUFU), ~2 ulp each.
   return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
 }
+// tanh through 2*sigmoid(2x) - 1 has an ABSOLUTE error of ~2e-7 (the subtraction cancels): fine for |x| ~ 1, but a
+// freshly re-initialised or weight-clipped network (CloudGAN, gan/common.py:44-64) runs its upper cells at
+// |z|, |c| ~ 1e-5, where that is percents of the value.  Below 2^-4 the odd Taylor polynomial x - x^3/3 + 2x^5/15 is
+// exact to 3e-9 relative; `t` is the formula's result for everything else.
+__device__ __forceinline__ float tanh_small_fix(float x, float t) {
+  const float x2 = x * x;
+  const float p = x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.f);
+  return fabsf(x) < 0.0625f ? p : t;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
-  // tanh(x) = 2*sigmoid(2x) - 1; absolute error ~1e-7, saturates cleanly.
-  return fmaf(2.0f, __fdividef(1.0f, 1.0f + exp2f(-2.8853900817779268f * x)), -1.0f);
+  // tanh(x) = 2*sigmoid(2x) - 1 (absolute error ~1e-7, saturates cleanly), polynomial for small |x|
+  return tanh_small_fix(x, fmaf(2.0f, __fdividef(1.0f, 1.0f + exp2f(-2.8853900817779268f * x)), -1.0f));
 }
 
 // Raw MUFU wrappers (flush-to-zero: callers clamp their arguments, so no denormal fix-up code is emitted).
@@ -257,7 +296,7 @@ __device__ __forceinline__ void lstm_gates_shared_rcp(float zi, float zf, float 
   gi = ra * df;
   gf = ra * di;
   go = rb * dg;
-  gg = fmaf(2.f, rb * dO, -1.f);
+  gg = tanh_small_fix(zg, fmaf(2.f, rb * dO, -1.f));
 }
 // tanh of two values with one reciprocal (arguments clamped to +-40: product below e^80).
 __device__ __forceinline__ void tanh_pair_shared_rcp(float xa, float xb, float& ta, float& tb) {
@@ -265,8 +304,8 @@ __device__ __forceinline__ void tanh_pair_shared_rcp(float xa, float xb, float& 
   const float da = 1.f + ex2_ftz(clampf(-2.f * xa, 40.f) * kL2e);
   const float db = 1.f + ex2_ftz(clampf(-2.f * xb, 40.f) * kL2e);
   const float r = rcp_ftz(da * db);
-  ta = fmaf(2.f, r * db, -1.f);
-  tb = fmaf(2.f, r * da, -1.f);
+  ta = tanh_small_fix(xa, fmaf(2.f, r * db, -1.f));
+  tb = tanh_small_fix(xb, fmaf(2.f, r * da, -1.f));
 }
 
 template <typename E>

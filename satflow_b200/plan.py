@@ -32,6 +32,11 @@ def _aligned_workspace(nbytes: int, device) -> torch.Tensor:
     return buf[off : off + nbytes]
 
 
+import itertools
+
+_USE_TICK = itertools.count(1)  # orders forwards across plans (which pending graph is the oldest)
+
+
 class RolloutPlan:
     """clstm_plan_t: one ConvLSTM.forward shape (conv_lstm.py:205-228) on one device."""
 
@@ -72,6 +77,7 @@ class RolloutPlan:
         # generation of the forward whose saved states are still in the workspace
         self.generation = 0
         self.pending_backward = False
+        self.last_use = 0
         # gradient range statistics of the last backwards (include/clstm.h clstm_plan_grad_status), fetched without
         # synchronising: a small ring of pinned host slots, each guarded by an event
         self.overflow_policy = "raise"  # "raise" | "ignore"
@@ -175,6 +181,7 @@ class RolloutPlan:
                 )
             )
         self.generation += 1
+        self.last_use = next(_USE_TICK)
         self.pending_backward = self.training
         return y
 
