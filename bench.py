@@ -514,18 +514,20 @@ def run_ours(args):
     peaks = measured_peaks()
     roof = None
     cpu = None
+    # (1) IN SITU: one CUDA event after every library launch of two more training steps (clstm_trace_enable), i.e.
+    # each kernel's average duration under the clocks and cache state of the real step -> sustained peak.  Every rank
+    # runs the steps (they contain the gradient all-reduce); only rank 0 records and reports.
     if rank == 0:
+        _lib.trace_enable(4096 * n_micro)
+    for _ in range(2):
+        train_step(x_dev, y_dev)
+    barrier()
+    if rank == 0:
+        tr = parse_trace(_lib.trace_report())
+        _lib.trace_enable(0)
         fl = cell_step_flops(B, hid, hid, HW, HW)  # a cell step with a 64-channel input: K = (64 + 64) * 9
         npix = B * HW * HW
         gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
-        # (1) IN SITU: one CUDA event after every library launch of two more training steps (clstm_trace_enable), i.e.
-        # each kernel's average duration under the clocks and cache state of the real step -> sustained peak.
-        _lib.trace_enable(4096)
-        for _ in range(2):
-            train_step(x_dev, y_dev)
-        torch.cuda.synchronize()
-        tr = parse_trace(_lib.trace_report())
-        _lib.trace_enable(0)
         tensor_kernels = {
             "cell_step": ("convgemm_kernel<EPI_LSTM>: fused conv + LSTM cell step (training variant, also writes gates)",
                           "convgemm_kernel<__half, 0>"),
@@ -695,13 +697,18 @@ def other_configs(ConvLSTM, ConvLSTMCell, dev, peaks):
 
             fl = cell_step_flops(1, hid, hid, px, px, k)
             ms_f, ms_fb = timeit(fwd, 10), timeit(fwd_bwd, 5)
+            stepper = cell.native(1, (px, px)).reset(h, c).set_input(x)  # state kept in the device layout
+            ms_n = timeit(stepper.step, 20)
+            stepper.close()
             cells.append({"kernel": f"{k}x{k}", "hidden": hid, "px": px, "fwd_ms": ms_f, "fwd_tflops": fl / ms_f / 1e9,
-                          "fwd_bwd_ms": ms_fb, "fwd_bwd_tflops": 3 * fl / ms_fb / 1e9})
+                          "fwd_bwd_ms": ms_fb, "fwd_bwd_tflops": 3 * fl / ms_fb / 1e9,
+                          "native_step_ms": ms_n, "native_step_tflops": fl / ms_n / 1e9})
             del cell, x, h, c, hg, cg
             torch.cuda.empty_cache()
         except Exception as e:
             cells.append({"kernel": f"{k}x{k}", "hidden": hid, "px": px, "error": str(e)[:200]})
-    out["configs[4] subset: ConvLSTMCell through the drop-in NCHW fp32 module API (B=1, Cin_x = hidden)"] = cells
+    out["configs[4] subset: ConvLSTMCell, B=1, Cin_x = hidden; fwd / fwd_bwd through the drop-in NCHW fp32 module API "
+        "(layout conversion on every call), native_step = ConvLSTMCell.native() (state kept in the device layout)"] = cells
     return out
 
 

@@ -159,6 +159,23 @@ int clstm_cell_forward(clstm_cell_plan_t* plan, const float* x, const float* h_c
 int clstm_cell_backward(clstm_cell_plan_t* plan, const float* dh_next, const float* dc_next, const float* weight,
                         float* dx, float* dh_cur, float* dc_cur, float* dweight, float* dbias, void* stream);
 
+/* ---- native-layout stepping of one cell (inference) ------------------------------------------------------------
+ * clstm_cell_forward converts x / h / c from the reference's NCHW fp32 to the kernels' NHWC 16-bit / fp32 layout and
+ * back on EVERY call — for a 64-channel cell at 256x256 that is more memory traffic than the cell step itself.  A
+ * caller that steps the same cell repeatedly (the loop of conv_lstm.py:176-183) can keep the recurrent state inside
+ * the plan instead:
+ *   clstm_cell_native_load  packs whatever is non-NULL: weight (+ bias) once, x (B,Cin,H,W) per step, h / c
+ *                           (B,hid,H,W) to seed the state; reset_state != 0 zero-fills the state first
+ *                           (ConvLSTMCell.init_hidden, layers/ConvLSTM.py:59-64);
+ *   clstm_cell_native_step  h, c <- ConvLSTMCell.forward(x, (h, c))  (layers/ConvLSTM.py:42-57): exactly one kernel;
+ *   clstm_cell_native_read  unpacks the current state to the reference layout (either pointer may be NULL).
+ * Results are bit-identical to chaining clstm_cell_forward.  No activations are kept: there is no backward on this path
+ * (use clstm_cell_forward / clstm_cell_backward or the rollout for training). */
+int clstm_cell_native_load(clstm_cell_plan_t* plan, const float* x, const float* h, const float* c, const float* weight,
+                           const float* bias, int reset_state, void* stream);
+int clstm_cell_native_step(clstm_cell_plan_t* plan, void* stream);
+int clstm_cell_native_read(clstm_cell_plan_t* plan, float* h_out, float* c_out, void* stream);
+
 /* ---- fused MSE loss + gradient (EncoderDecoderConvLSTM.training_step, conv_lstm.py:55-69) --------------------
  * y (B,C,T,H,W) = the rollout output, target (B,T,C,H,W) as the reference's batches; writes
  *   out[0] = mean((permute(y) - target)^2), out[1 + t] = the same mean over frame t (the reference's per-frame

@@ -6,7 +6,7 @@ Drop-in surface: ``ConvLSTMCell``, ``ConvLSTM``, ``EncoderDec
 CPU or eager fallback.
 """
 from .registry import create_model, get_model, is_model, list_models, register_model  # noqa: F401
-from .layers import ConvLSTMCell, get_conv_layer  # noqa: F401
+from .layers import ConvLSTMCell, NativeCellStepper, get_conv_layer  # noqa: F401
 from .conv_lstm import ConvLSTM, EncoderDecoderConvLSTM, get_loss  # noqa: F401
 from .plan import CellPlan, RolloutPlan  # noqa: F401
 from .loss import fused_mse  # noqa: F401

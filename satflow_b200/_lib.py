@@ -68,6 +68,9 @@ _PROTOTYPES = {
     "clstm_cell_plan_bind_split": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "clstm_cell_forward": (c_int, [c_void_p] + [c_void_p] * 7 + [c_void_p]),
     "clstm_cell_backward": (c_int, [c_void_p] + [c_void_p] * 8 + [c_void_p]),
+    "clstm_cell_native_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "clstm_cell_native_step": (c_int, [c_void_p, c_void_p]),
+    "clstm_cell_native_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_mse_loss_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "clstm_launch_count": (c_uint64, []),
     "clstm_trace_enable": (c_int, [c_int]),

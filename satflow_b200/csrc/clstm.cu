@@ -96,7 +96,8 @@ struct Knobs {
   int stages = kMaxStages;  // CLSTM_STAGES: cap on the operand ring depth of the conv GEMM
   int rotate = 1;           // CLSTM_ROTATE: per-tile rotated K loop in the conv GEMM
   int rotate_d = 0;         // CLSTM_ROTATE_D: the same in dgradT (measured: no gain)
-  int staged = 1;           // CLSTM_STAGED: shared-memory staged TMA-store epilogue (0: direct per-thread stores)
+  int staged = 1;           // CLSTM_STAGED: shared-memory staged TMA-store epilogue (0: direct per-thread stores;
+                            // 2: 8-channel groups + c_prev in registers -> a fourth operand stage fits)
   int dgradT = 1;           // CLSTM_DGRADT: transposed dgrad (0: pixel-major dgrad through convgemm)
   int fuse_gate = 1;        // CLSTM_FUSE_GATE: gate gradient fused into the dgrad epilogue
   int fuse_pf = 1;          // CLSTM_FUSE_PF: its L2 prefetch distance in groups
@@ -200,8 +201,10 @@ int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, i
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const int row_bytes = box_c * elem_bytes;
-  const CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw =
+      row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                       : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                          : (row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                            : (dtype16 == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                    : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
@@ -327,6 +330,7 @@ struct CellState {
   CUtensorMap m_h66;                                // wgrad halo rows: box 64 ch x 66 px x 1 row
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
+  CUtensorMap m_c8, m_h8, m_g8;                     // the same with 8-channel boxes (CLSTM_STAGED=2)
 
   size_t h_slot_elems(const Geo& geo) const { return geo.npix() * g.HP; }
 };
@@ -418,6 +422,12 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
                       g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
+  RC_TRY(make_map_epi(&cs.m_c8, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW, g.BH,
+                      8));
+  RC_TRY(make_map_epi(&cs.m_h8, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH, 8));
+  if (ctx.training)
+    RC_TRY(make_map_epi(&cs.m_g8, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B, g.BW,
+                        g.BH, 8));
   if (ctx.training) {
     RC_TRY(make_map_epi(&cs.m_g16, 2, ctx.dtype, cs.gates, 4 * ctx.HP, g.W, g.H, static_cast<long long>(cs.T) * g.B,
                         g.BW, g.BH));
@@ -435,19 +445,22 @@ template <typename E, int EPI>
 int launch_convgemm(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                     ConvGemmParams p, const Geo& g, long long images, cudaStream_t st,
                     const CUtensorMap* x0 = nullptr, const CUtensorMap* x1 = nullptr, const CUtensorMap* x2 = nullptr,
-                    const CUtensorMap* x3 = nullptr, const char* name = "convgemm_kernel") {
+                    const CUtensorMap* x3 = nullptr, const char* name = "convgemm_kernel", const CUtensorMap* x4 = nullptr,
+                    const CUtensorMap* x5 = nullptr, const CUtensorMap* x6 = nullptr) {
   p.B = static_cast<int>(images), p.H = g.H, p.W = g.W;
   p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
   p.num_m_tiles = static_cast<int>(images) * g.tiles_w * g.tiles_h;
   const DeviceInfo& dev = cx.dev;
   // staged epilogue: outputs go through swizzled shared memory + TMA stores (0: direct per-thread stores)
   p.staged = (x0 != nullptr && EPI != EPI_HEAD && cx.knobs.staged) ? 1 : 0;
+  if (p.staged && EPI == EPI_LSTM && cx.knobs.staged == 2 && x4 != nullptr) p.staged = 2;
   {
     int kblocks = 0;
     for (int s = 0; s < p.nseg; ++s) kblocks += p.seg[s].chunks * p.seg[s].kh * p.seg[s].kw;
     p.rotate = (kblocks <= kKtabMax && kblocks > 1 && cx.knobs.rotate) ? 1 : 0;
   }
-  const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
+  const int stg_half = p.staged ? stg_half_bytes(EPI, p.staged) : 0;
+  if (p.staged == 2) x0 = x4, x1 = x5, x2 = x6, x3 = nullptr;  // the 8-channel-box maps
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int fixed = static_cast<int>(convgemm_smem_bytes(0, p.n_tile, p.n_tiles, stg_half));
   int stages = (dev.smem_optin - fixed) / stage_bytes;
@@ -681,7 +694,8 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
     p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
     return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
                                         &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16, nullptr,
-                                        g.in_col ? "cell_step[x im2col]" : "cell_step");
+                                        g.in_col ? "cell_step[x im2col]" : "cell_step", &cs.m_c8, &cs.m_h8,
+                                        ctx.training ? &cs.m_g8 : &cs.m_h8);
   }
   return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, nullptr, nullptr,
                                       nullptr, nullptr, "cell_step[direct stores]");
@@ -1411,6 +1425,8 @@ struct clstm_cell_plan {
   int cin = 0, hid = 0;
   size_t saved_bytes = 0, scratch_bytes = 0;
   bool bound = false, forward_done = false;
+  int cur = 0;          // native stepping: slot (0 / 1) holding the current h / c state
+  bool native_ready = false;
   void* xin = nullptr;  // E [npix][CIP]
   CUtensorMap m_x128, m_x64;
 };
@@ -1466,6 +1482,76 @@ int cellplan_forward(clstm_cell_plan* p, const float* x, const float* h_cur, con
     RC_TRY(after_launch("unpack_nchw_kernel"));
   }
   p->forward_done = true;
+  return 0;
+}
+
+// ---- native-layout stepping (clstm_cell_native_*): the state stays in the plan's NHWC 16-bit / fp32 slots between
+// steps, the weights are packed once, so one step is exactly one fused kernel (no NCHW <-> NHWC packing).
+template <typename E>
+int cellplan_native_load(clstm_cell_plan* p, const float* x, const float* h, const float* c, const float* weight,
+                         const float* bias, int reset_state, cudaStream_t st) {
+  Ctx& ctx = p->ctx;
+  CellState& cs = p->cs;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  const size_t plane = static_cast<size_t>(geo.H) * geo.W;
+  if (weight) RC_TRY(pack_cell<E>(ctx, cs, weight, bias, st));
+  if (x) {
+    pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(x, static_cast<E*>(p->xin), geo.B, p->cin, geo.H, geo.W, cs.g.CIP,
+                                                     p->cin * plane, 1.f);
+    RC_TRY(after_launch("pack_nhwc_kernel"));
+  }
+  E* hcur = static_cast<E*>(cs.h) + static_cast<size_t>(p->cur) * npix * HP;
+  float* ccur = cs.c + static_cast<size_t>(p->cur) * npix * HP;
+  if (h) {
+    pack_nhwc_kernel<E><<<kPackBlocks, 256, 0, st>>>(h, hcur, geo.B, p->hid, geo.H, geo.W, HP, p->hid * plane, kHScale);
+    RC_TRY(after_launch("pack_nhwc_kernel"));
+  } else if (reset_state) {
+    CU_TRY(cudaMemsetAsync(hcur, 0, npix * HP * sizeof(E), st));  // ConvLSTMCell.init_hidden (layers/ConvLSTM.py:59-64)
+  }
+  if (c) {
+    pack_nhwc_f32_kernel<<<kPackBlocks, 256, 0, st>>>(c, ccur, geo.B, p->hid, geo.H, geo.W, HP, nullptr);
+    RC_TRY(after_launch("pack_nhwc_f32_kernel"));
+  } else if (reset_state) {
+    CU_TRY(cudaMemsetAsync(ccur, 0, npix * HP * 4, st));
+  }
+  return 0;
+}
+
+template <typename E>
+int cellplan_native_step(clstm_cell_plan* p, cudaStream_t st) {
+  Ctx& ctx = p->ctx;
+  CellState& cs = p->cs;
+  const size_t npix = ctx.geo.npix();
+  const int HP = ctx.HP;
+  InputRef in;
+  in.map128 = &p->m_x128, in.map64 = &p->m_x64, in.b_off = 0;
+  const int a = p->cur, b = p->cur ^ 1;
+  // gates == nullptr: nothing is kept for a backward, the step writes only h' and c'
+  RC_TRY(cell_forward_step<E>(ctx, cs, in, a, b, cs.c + static_cast<size_t>(a) * npix * HP,
+                              cs.c + static_cast<size_t>(b) * npix * HP, nullptr, st, a, b, -1));
+  p->cur = b;
+  return 0;
+}
+
+template <typename E>
+int cellplan_native_read(clstm_cell_plan* p, float* h_out, float* c_out, cudaStream_t st) {
+  Ctx& ctx = p->ctx;
+  CellState& cs = p->cs;
+  const Geo& geo = ctx.geo;
+  const size_t npix = geo.npix();
+  const int HP = ctx.HP;
+  if (h_out) {
+    unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(static_cast<const E*>(cs.h) + static_cast<size_t>(p->cur) * npix * HP,
+                                                       h_out, geo.B, p->hid, geo.H, geo.W, HP, nullptr, 0, kHScaleInv);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
+  if (c_out) {
+    unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(cs.c + static_cast<size_t>(p->cur) * npix * HP, c_out, geo.B,
+                                                           p->hid, geo.H, geo.W, HP, nullptr, 0);
+    RC_TRY(after_launch("unpack_nchw_kernel"));
+  }
   return 0;
 }
 
@@ -1951,6 +2037,38 @@ int clstm_cell_forward(clstm_cell_plan_t* p, const float* x, const float* h_cur,
   if (!p->bound) return fail(CLSTM_ESTATE, "clstm_cell_forward before clstm_cell_plan_bind");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL_(E) cellplan_forward<E>(p, x, h_cur, c_cur, weight, bias, h_next, c_next, st)
+  return DISPATCH_E(p->ctx.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_cell_native_load(clstm_cell_plan_t* p, const float* x, const float* h, const float* c, const float* weight,
+                           const float* bias, int reset_state, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound) return fail(CLSTM_ESTATE, "clstm_cell_native_load before clstm_cell_plan_bind");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (reset_state) p->cur = 0;
+#define CALL_(E) cellplan_native_load<E>(p, x, h, c, weight, bias, reset_state, st)
+  RC_TRY(DISPATCH_E(p->ctx.dtype, CALL_));
+#undef CALL_
+  if (weight) p->native_ready = true;
+  return 0;
+}
+
+int clstm_cell_native_step(clstm_cell_plan_t* p, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound || !p->native_ready)
+    return fail(CLSTM_ESTATE, "clstm_cell_native_step needs a bound plan and weights (clstm_cell_native_load)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) cellplan_native_step<E>(p, st)
+  return DISPATCH_E(p->ctx.dtype, CALL_);
+#undef CALL_
+}
+
+int clstm_cell_native_read(clstm_cell_plan_t* p, float* h_out, float* c_out, void* stream) {
+  if (!p) return fail(CLSTM_EINVAL, "null argument");
+  if (!p->bound) return fail(CLSTM_ESTATE, "clstm_cell_native_read before clstm_cell_plan_bind");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL_(E) cellplan_native_read<E>(p, h_out, c_out, st)
   return DISPATCH_E(p->ctx.dtype, CALL_);
 #undef CALL_
 }

@@ -35,8 +35,13 @@ constexpr int kKtabMax = 64;       // k-block table entries (rotated K loop)
 constexpr int kStgCprev = 0, kStgC = 8192, kStgH = 16384, kStgG = 20480;
 constexpr int kStgHalfLstm = 36864;   // EPI_LSTM
 constexpr int kStgHalfStore = 8192;   // EPI_STORE: one fp32 [128 x 16] group
-__host__ __device__ constexpr int stg_half_bytes(int epi) {
-  return epi == 0 /*EPI_LSTM*/ ? kStgHalfLstm : (epi == 1 /*EPI_STORE*/ ? kStgHalfStore : 0);
+// EPI_LSTM with 8-channel groups (staged == 2): [c 4 KB][h 2 KB][gates 4 x 2 KB]; c_prev goes straight to registers.
+// 28 KB of staging instead of 72 KB is what a FOURTH 48 KB operand stage needs (DESIGN.md finding 8: the 3-stage ring
+// has no slack).
+constexpr int kStg8C = 0, kStg8H = 4096, kStg8G = 6144;
+constexpr int kStgHalfLstm8 = 14336;
+__host__ __device__ constexpr int stg_half_bytes(int epi, int staged = 1) {
+  return epi == 0 /*EPI_LSTM*/ ? (staged == 2 ? kStgHalfLstm8 : kStgHalfLstm) : (epi == 1 /*EPI_STORE*/ ? kStgHalfStore : 0);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -69,7 +74,8 @@ struct ConvGemmParams {
   void* gates;          // E    [pixel][4*ldc] ([i|f|o|g] blocks of ldc) or nullptr
   int ldc;              // padded hidden channels (multiple of 64)
   // staged epilogue (TMA stores / c_prev TMA load): image offsets into the epilogue tensor maps
-  int staged;           // 1: outputs go through shared memory + TMA (tmX0..tmX2), 0: direct per-thread stores
+  int staged;           // 1: outputs go through shared memory + TMA (tmX0..tmX2), 0: direct per-thread stores,
+                        // 2 (EPI_LSTM): the same in 8-channel groups with c_prev read straight into registers
   int cprev_boff, cnext_boff, hnext_boff, gates_boff;
   // ---- EPI_STORE
   float* out0;
@@ -206,7 +212,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kABytes + p.n_tile * 128;
   uint8_t* smem_stg = smem + p.stages * stage_bytes;  // epilogue staging (1024-aligned: stage_bytes is)
-  const int stg_half = p.staged ? stg_half_bytes(EPI) : 0;
+  const int stg_half = p.staged ? stg_half_bytes(EPI, p.staged) : 0;
   uint8_t* tail = smem_stg + 2 * stg_half;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -392,7 +398,98 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
         b = mt / (p.tiles_w * p.tiles_h);
       };
-      if constexpr (EPI == EPI_LSTM) {
+      if (EPI == EPI_LSTM && p.staged == 2) {
+        // ---- 8-channel groups.  Per half: 4 groups per tile; c_prev of the whole tile (32 floats per thread) is
+        // requested from global memory BEFORE the wait for the accumulator, so its latency hides behind the MMAs.
+        const bool has_cprev = p.c_prev != nullptr;
+        const int lbw = 31 - __clz(p.BW);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int nt, w0, h0, b;
+          coords(tile, nt, w0, h0, b);
+          float4 cpv[4][2];
+          {
+            const int hy = h0 + (r >> lbw), wx = w0 + (r & (p.BW - 1));
+            const bool valid = has_cprev && hy < p.H && wx < p.W;
+            const float* src = p.c_prev + ((static_cast<size_t>(b) * p.H + hy) * p.W + wx) * p.ldc + nt * 64 + half * 32;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                cpv[g4][j] = valid ? __ldg(reinterpret_cast<const float4*>(src + g4 * 8 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+          const float* bs = bias_s + nt * 256;
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int j0 = half * 32 + g4 * 8;
+            uint32_t vi[8], vf[8], vo[8], vg[8];
+            tmem_ld8(taddr + 0 + j0, vi);
+            tmem_ld8(taddr + 64 + j0, vf);
+            tmem_ld8(taddr + 128 + j0, vo);
+            tmem_ld8(taddr + 192 + j0, vg);
+            if (q == 0 && lane < 6) tma_store_wait_read();  // this lane's previous store has finished reading staging
+            named_bar_sync(bar_id, 128);
+            tmem_ld_wait();
+            const float cp[8] = {cpv[g4][0].x, cpv[g4][0].y, cpv[g4][0].z, cpv[g4][0].w,
+                                 cpv[g4][1].x, cpv[g4][1].y, cpv[g4][1].z, cpv[g4][1].w};
+            float cn[8], hn[8], gi[8], gf[8], go[8], gg[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              lstm_gates_shared_rcp(fmaf(__uint_as_float(vi[e]), kHScaleInv, bs[0 + j0 + e]),
+                                    fmaf(__uint_as_float(vf[e]), kHScaleInv, bs[64 + j0 + e]),
+                                    fmaf(__uint_as_float(vo[e]), kHScaleInv, bs[128 + j0 + e]),
+                                    fmaf(__uint_as_float(vg[e]), kHScaleInv, bs[192 + j0 + e]), gi[e], gf[e], go[e], gg[e]);
+              cn[e] = fmaf(gf[e], cp[e], gi[e] * gg[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float ta, tb;
+              tanh_pair_shared_rcp(cn[e], cn[e + 1], ta, tb);
+              hn[e] = go[e] * ta * kHScale;
+              hn[e + 1] = go[e + 1] * tb * kHScale;
+            }
+            if (g4 == 3) {  // all TMEM reads of this accumulator are done
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            auto pack8 = [](const float* v) {
+              return make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]), Elem<E>::pack2(v[4], v[5]),
+                                Elem<E>::pack2(v[6], v[7]));
+            };
+            // c: 32-byte rows, SWIZZLE_32B; h / gates: 16-byte rows, dense (thread r owns row r: conflict free)
+#pragma unroll
+            for (uint32_t j = 0; j < 2; ++j)
+              *reinterpret_cast<float4*>(stg + kStg8C + r * 32 + ((j ^ x32) << 4)) =
+                  make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+            *reinterpret_cast<uint4*>(stg + kStg8H + r * 16) = pack8(hn);
+            if (p.gates_boff >= 0) {
+              *reinterpret_cast<uint4*>(stg + kStg8G + 0 * 2048 + r * 16) = pack8(gi);
+              *reinterpret_cast<uint4*>(stg + kStg8G + 1 * 2048 + r * 16) = pack8(gf);
+              *reinterpret_cast<uint4*>(stg + kStg8G + 2 * 2048 + r * 16) = pack8(go);
+              *reinterpret_cast<uint4*>(stg + kStg8G + 3 * 2048 + r * 16) = pack8(gg);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (q == 0 && lane < 6) {
+              const int chan = nt * 64 + j0;
+              if (lane == 0) {
+                tma_store_4d(&tmX0, stg + kStg8C, chan, w0, h0, b + p.cnext_boff);
+              } else if (lane == 1) {
+                tma_store_4d(&tmX1, stg + kStg8H, chan, w0, h0, b + p.hnext_boff);
+              } else if (p.gates_boff >= 0) {
+                const int gt = lane - 2;
+                tma_store_4d(&tmX2, stg + kStg8G + gt * 2048, gt * p.ldc + chan, w0, h0, b + p.gates_boff);
+              }
+              tma_store_commit();
+            }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      } else if constexpr (EPI == EPI_LSTM) {
         const bool has_cprev = p.cprev_boff >= 0;
         uint32_t cp_phase = 0;
         if (issuer && has_cprev && static_cast<int>(blockIdx.x) < total_tiles) {

@@ -49,6 +49,59 @@ class _CellFn(torch.autograd.Function):
         return None, dx, dhp, dcp, dw, db
 
 
+class NativeCellStepper:
+    """Inference stepping of one ConvLSTMCell with the recurrent state kept in the kernels' native layout (NHWC,
+    16-bit h, fp32 c) inside the device plan: weights are packed once, and one ``step`` is exactly one fused kernel
+    instead of pack x/h/c -> kernel -> unpack h/c (include/clstm.h "native-layout stepping").  Bit-identical to chaining
+    ``ConvLSTMCell.forward`` (layers/ConvLSTM.py:42-57) under ``torch.no_grad()``; no autograd on this path.
+
+        stepper = cell.native(batch, (H, W))          # zero state (init_hidden)
+        for t in range(T):
+            stepper.step(x[:, t])
+        h, c = stepper.state()                        # (B, hid, H, W) float32, reference layout
+    """
+
+    def __init__(self, cell: "ConvLSTMCell", batch_size: int, image_size, device=None):
+        H, W = image_size
+        self.cell = cell
+        dev = cell.conv.weight.device if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("satflow_b200.ConvLSTMCell.native runs on a B200 only; move the cell to cuda first")
+        self.plan = CellPlan(batch_size, H, W, cell.input_dim, cell.hidden_dim, tuple(cell.kernel_size), cell.operand_dtype, dev)
+        self.refresh_weights()
+        self.reset()
+
+    def refresh_weights(self) -> None:
+        """Re-pack the cell's current parameters (call after an optimizer step / load_state_dict)."""
+        self.plan.native_load(weight=self.cell.conv.weight.detach(),
+                              bias=None if self.cell.conv.bias is None else self.cell.conv.bias.detach())
+
+    def reset(self, h: torch.Tensor = None, c: torch.Tensor = None) -> "NativeCellStepper":
+        """Zero state (``init_hidden``), optionally seeded with reference-layout h / c."""
+        self.plan.native_load(h=h, c=c, reset=True)
+        return self
+
+    def set_input(self, x: torch.Tensor) -> "NativeCellStepper":
+        B, H, W, cin, _ = self.plan.shape
+        if tuple(x.shape) != (B, cin, H, W):
+            raise RuntimeError(f"expected input {(B, cin, H, W)}, got {tuple(x.shape)}")
+        self.plan.native_load(x=x.float())
+        return self
+
+    def step(self, x: torch.Tensor = None) -> "NativeCellStepper":
+        """h, c <- cell(x, (h, c)).  ``x=None`` re-uses the input packed last (e.g. timing the bare cell step)."""
+        if x is not None:
+            self.set_input(x)
+        self.plan.native_step()
+        return self
+
+    def state(self):
+        return self.plan.native_read()
+
+    def close(self) -> None:
+        self.plan.close()
+
+
 class ConvLSTMCell(nn.Module):
     def __init__(self, input_dim: int, hidden_dim: int, kernel_size: Tuple[int, int], bias: bool, conv_type: str = "standard"):
         super().__init__()
@@ -91,6 +144,10 @@ class ConvLSTMCell(nn.Module):
         plan = self._plan(input_tensor)
         h_next, c_next = _CellFn.apply(plan, input_tensor, h_cur, c_cur, self.conv.weight, self.conv.bias)
         return h_next, c_next
+
+    def native(self, batch_size: int, image_size) -> NativeCellStepper:
+        """Inference stepper that keeps h / c in the device layout between steps (no per-call layout conversion)."""
+        return NativeCellStepper(self, batch_size, image_size)
 
     def init_hidden(self, batch_size, image_size):
         height, width = image_size

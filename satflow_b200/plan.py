@@ -313,6 +313,37 @@ class CellPlan:
             )
         return hn, cn, saved
 
+    # ---- native-layout stepping (include/clstm.h clstm_cell_native_*): inference, state kept in the plan ----
+    def native_bind(self) -> None:
+        if self._shared_saved is None:
+            self._shared_saved = _aligned_workspace(self.saved_bytes, self.device)
+        with torch.cuda.device(self.device):
+            self._bind(self._shared_saved)
+
+    def native_load(self, x=None, h=None, c=None, weight=None, bias=None, reset: bool = False) -> None:
+        keep = [None if t is None else t.contiguous() for t in (x, h, c, weight, bias)]
+        for name, t in zip(("x", "h", "c", "weight", "bias"), keep):
+            if t is not None:
+                _require_cuda(t, name)
+        with torch.cuda.device(self.device):
+            self.native_bind()
+            _lib.check(_lib.lib().clstm_cell_native_load(self._h, *[_lib.ptr(t) for t in keep], int(reset),
+                                                         _stream_ptr(self.device)))
+
+    def native_step(self) -> None:
+        with torch.cuda.device(self.device):
+            self.native_bind()
+            _lib.check(_lib.lib().clstm_cell_native_step(self._h, _stream_ptr(self.device)))
+
+    def native_read(self):
+        B, H, W, _, hid = self.shape
+        h = torch.empty(B, hid, H, W, dtype=torch.float32, device=self.device)
+        c = torch.empty_like(h)
+        with torch.cuda.device(self.device):
+            self.native_bind()
+            _lib.check(_lib.lib().clstm_cell_native_read(self._h, _lib.ptr(h), _lib.ptr(c), _stream_ptr(self.device)))
+        return h, c
+
     def backward(self, saved, dh, dc, weight, need_bias=True):
         B, H, W, cin, hid = self.shape
         dev = self.device
