@@ -113,6 +113,14 @@ int clstm_rollout_backward(clstm_plan_t* plan, const float* dy, const float* y, 
  * of that backward are not usable.  The caller decides when to look (satflow_b200 checks it without synchronising). */
 int clstm_plan_grad_status(clstm_plan_t* plan, float* out4, void* stream);
 
+/* How the plan executes (decided at bind time from the shape; DESIGN.md "Small shapes"):
+ *   CLSTM_INFO_PERSISTENT_CHAIN  1 if the forward chain of cell steps (conv_lstm.py:176-196) runs as ONE persistent
+ *                                launch with the cell states resident in TMEM (every tile has its own CTA), else 0;
+ *   CLSTM_INFO_GRAPH_ENABLED     1 if launch-bound forward / backward calls are replayed as CUDA graphs;
+ *   CLSTM_INFO_GRAPH_CAPTURES / _REPLAYS   how many graphs were captured / how many calls were replays so far. */
+enum { CLSTM_INFO_PERSISTENT_CHAIN = 0, CLSTM_INFO_GRAPH_ENABLED = 1, CLSTM_INFO_GRAPH_CAPTURES = 2, CLSTM_INFO_GRAPH_REPLAYS = 3 };
+int clstm_plan_info(const clstm_plan_t* plan, int what, long long* out);
+
 /* Read back a recurrent state in the reference layout (B,hid,H,W) fp32: cell in [0,2L),
  * step in [0,T_cell] where 0 is the zero initial state and T_cell the final state.
  * Either output may be NULL.  In inference plans only the last two c steps are retained. */

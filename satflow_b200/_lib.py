@@ -57,6 +57,7 @@ _PROTOTYPES = {
     "clstm_rollout_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "clstm_rollout_backward": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_void_p]),
     "clstm_plan_grad_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "clstm_plan_info": (c_int, [c_void_p, c_int, POINTER(ctypes.c_longlong)]),
     "clstm_plan_read_state": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "clstm_plan_profile_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "clstm_cell_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),

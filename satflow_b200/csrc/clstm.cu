@@ -20,6 +20,7 @@
 #include "../../include/clstm.h"
 #include "convgemm.cuh"
 #include "dgradT.cuh"
+#include "dgradT_fused2.cuh"
 #include "head_rows.cuh"
 #include "pointwise.cuh"
 #include "rollout_persist.cuh"
@@ -101,14 +102,20 @@ struct Knobs {
   int dgradT = 1;           // CLSTM_DGRADT: transposed dgrad (0: pixel-major dgrad through convgemm)
   int fuse_gate = 1;        // CLSTM_FUSE_GATE: gate gradient fused into the dgrad epilogue
   int fuse_pf = 1;          // CLSTM_FUSE_PF: its L2 prefetch distance in groups
-  int fuse_teams = 2;       // CLSTM_FUSE_TEAMS: its epilogue teams (2 or 4)
+  int fuse_sets = 4;        // CLSTM_FUSE_SETS: register sets of loads in flight per epilogue thread (2; 4 = setmaxnreg)
+  int fuse_workers = 2;     // CLSTM_FUSE_WORKERS: gate gradient on dedicated worker warps (dgradT_fused2.cuh) with this
+                            // many register sets of loads in flight (2 or 4); 0 = the epilogue warps do it themselves
   int head_rows = 1;        // CLSTM_HEAD_ROWS: row-marching output head (0: implicit-GEMM head)
   int head_band = 32;       // CLSTM_HEAD_BAND: rows per band of the row-marching head
   int wg_halo = 1;          // CLSTM_WG_HALO: halo-row wgrad
   int wg_gate = 0;          // CLSTM_WG_GATE: gate gradient on worker warps inside wgrad (1: plain, 2: setmaxnreg)
+  int hybrid_pct = 0;       // CLSTM_HYBRID: percent of the pixels whose gate gradient stays in the dgrad epilogue, the rest
+                            // runs on worker warps of the following wgrad launch (0 = off: all in the dgrad epilogue)
+  int hybrid_wg = 2;        // CLSTM_HYBRID_WG: which wgrad worker variant the hybrid schedule uses (1 or 2)
   int wg_group = kWgMaxGroupBlocks;  // CLSTM_WG_GROUP: column blocks per wgrad CTA
   int overlap = 0;          // CLSTM_OVERLAP: wgrad on a side stream
   int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
+  int graph = 1;            // CLSTM_GRAPH: launch-bound (small) rollouts replay their forward / backward as CUDA graphs
   void read() {
     stages = env_int("CLSTM_STAGES", stages);
     rotate = env_int("CLSTM_ROTATE", rotate);
@@ -117,20 +124,119 @@ struct Knobs {
     dgradT = env_int("CLSTM_DGRADT", dgradT);
     fuse_gate = env_int("CLSTM_FUSE_GATE", fuse_gate);
     fuse_pf = env_int("CLSTM_FUSE_PF", fuse_pf);
-    fuse_teams = env_int("CLSTM_FUSE_TEAMS", fuse_teams);
+    fuse_sets = env_int("CLSTM_FUSE_SETS", fuse_sets);
+    fuse_workers = env_int("CLSTM_FUSE_WORKERS", fuse_workers);
     head_rows = env_int("CLSTM_HEAD_ROWS", head_rows);
     head_band = env_int("CLSTM_HEAD_BAND", head_band);
     wg_halo = env_int("CLSTM_WG_HALO", wg_halo);
     wg_gate = env_int("CLSTM_WG_GATE", wg_gate);
+    hybrid_pct = env_int("CLSTM_HYBRID", hybrid_pct);
+    hybrid_wg = env_int("CLSTM_HYBRID_WG", hybrid_wg);
     wg_group = env_int("CLSTM_WG_GROUP", wg_group);
     if (wg_group < 1 || wg_group > kWgMaxGroupBlocks) wg_group = kWgMaxGroupBlocks;
     overlap = env_int("CLSTM_OVERLAP", overlap);
     persist = env_int("CLSTM_PERSIST", persist);
+    graph = env_int("CLSTM_GRAPH", graph);
   }
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------- CUDA-graph replay of launch-bound calls
+// A small rollout (BASELINE configs[0]: 64x64, batch 2) is ~75 launches of a few microseconds each per backward: the
+// host cannot enqueue them as fast as the GPU retires them (measured: 1.5 ms of enqueue for 1.8 ms of step).  The
+// sequence of launches of one API call depends only on the plan and on the pointers passed in, so it is captured once
+// per distinct pointer set (stream capture of the very same host code) and replayed with one cudaGraphLaunch.
+// PyTorch's caching allocator hands a training loop the same blocks every iteration, so the pointer sets repeat.
+// A key is captured the SECOND time it is seen (one-off calls never pay for an instantiation); at most kMaxGraphs
+// executables are kept per call site (LRU); any capture failure disables the cache for the plan and runs eagerly.
+struct GraphCache {
+  static constexpr size_t kMaxGraphs = 4;
+  struct Entry {
+    std::vector<const void*> key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last = 0;
+    uint64_t launches = 0;  // kernels in the graph (keeps clstm_launch_count meaningful across replays)
+  };
+  std::vector<Entry> entries;
+  std::vector<std::vector<const void*>> seen;  // keys run eagerly once (small ring)
+  uint64_t tick = 0, replays = 0, captures = 0;
+  bool disabled = false;
+  // Capture happens on a private stream: the caller's stream may be the legacy default stream (PyTorch's current
+  // stream usually is), which cannot be captured; the instantiated graph is then launched on the caller's stream.
+  cudaStream_t capture_stream = nullptr;
+  void clear() {
+    for (Entry& e : entries)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+    entries.clear();
+    seen.clear();
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+    capture_stream = nullptr;
+  }
+};
+
+template <typename F>
+int run_graphed(GraphCache& gc, bool enabled, std::vector<const void*> key, cudaStream_t st, F&& body) {
+  if (!enabled || gc.disabled || g_trace.on) return body(st);
+  ++gc.tick;
+  for (GraphCache::Entry& e : gc.entries)
+    if (e.key == key) {
+      e.last = gc.tick;
+      ++gc.replays;
+      CU_TRY(cudaGraphLaunch(e.exec, st));
+      g_launches.fetch_add(e.launches, std::memory_order_relaxed);
+      return 0;
+    }
+  bool seen_before = false;
+  for (const auto& k : gc.seen) seen_before = seen_before || (k == key);
+  if (!seen_before) {
+    if (gc.seen.size() >= 8) gc.seen.erase(gc.seen.begin());
+    gc.seen.push_back(key);
+    return body(st);
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body(st);  // the caller is capturing this stream itself
+  }
+  if (!gc.capture_stream && cudaStreamCreateWithFlags(&gc.capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    gc.disabled = true;
+    return body(st);
+  }
+  if (cudaStreamBeginCapture(gc.capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    gc.disabled = true;
+    return body(st);
+  }
+  const uint64_t l0 = g_launches.load();
+  const int rc = body(gc.capture_stream);
+  const uint64_t captured_launches = g_launches.load() - l0;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(gc.capture_stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    gc.disabled = true;
+    return rc != 0 ? rc : body(st);  // nothing was executed during the capture
+  }
+  cudaGraphDestroy(graph);
+  if (gc.entries.size() >= GraphCache::kMaxGraphs) {
+    size_t lru = 0;
+    for (size_t i = 1; i < gc.entries.size(); ++i)
+      if (gc.entries[i].last < gc.entries[lru].last) lru = i;
+    cudaGraphExecDestroy(gc.entries[lru].exec);
+    gc.entries.erase(gc.entries.begin() + static_cast<long>(lru));
+  }
+  GraphCache::Entry e;
+  e.key = std::move(key), e.exec = exec, e.last = gc.tick, e.launches = captured_launches;
+  gc.entries.push_back(std::move(e));
+  ++gc.captures;
+  CU_TRY(cudaGraphLaunch(exec, st));
+  return 0;
+}
 
 // --------------------------------------------------------------------------- device / driver
 struct DeviceInfo {
@@ -519,8 +625,9 @@ int launch_dgradT(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT
 
 // Transposed dgrad whose epilogue also runs the gate gradient of the NEXT cell step of the backward chain.
 template <typename E>
-int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x1,
-                        const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f, cudaStream_t st) {
+int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
+                        const CUtensorMap& x1, const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f,
+                        cudaStream_t st) {
   const DeviceInfo& dev = cx.dev;
   DgradTParams p;
   memset(&p, 0, sizeof(p));
@@ -538,16 +645,35 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
   p.stages = stages;
   const int units = (p.num_m_tiles + 1) / 2;
   const int grid = units < dev.sms ? units : dev.sms;
+  if ((cx.knobs.fuse_workers == 2 || cx.knobs.fuse_workers == 4) && f.src2 == nullptr && f.fuse_units >= units) {
+    // second generation: drain warps + gate-gradient worker warps meeting at a staging ring (3 operand stages)
+    int st2 = (dev.smem_optin - static_cast<int>(dgradTf2_smem_bytes(0))) / kDtStageBytes;
+    if (st2 > kMaxStages) st2 = kMaxStages;
+    if (st2 >= 2) {
+      p.stages = st2;
+      static bool attr2_set = false;
+      if (!attr2_set) {
+        CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
+        CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
+        attr2_set = true;
+      }
+      if (cx.knobs.fuse_workers == 4)
+        dgradT_fused2_kernel<E, 4><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, p, f);
+      else
+        dgradT_fused2_kernel<E, 2><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, p, f);
+      return after_launch("dgradT_fused2_kernel");
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
-    CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    CU_TRY((cudaFuncSetAttribute(dgradT_fused_kernel<E, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
     attr_set = true;
   }
-  if (cx.knobs.fuse_teams == 4)
-    dgradT_fused_kernel<E, 4><<<grid, 128 + 4 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
+  if (cx.knobs.fuse_sets == 4)
+    dgradT_fused_kernel<E, 2, 4><<<grid, 128 + 2 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x0, x1, p, f);
   else
-    dgradT_fused_kernel<E, 2><<<grid, 128 + 2 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x1, p, f);
+    dgradT_fused_kernel<E, 2><<<grid, 128 + 2 * 128, dgradTf_smem_bytes(stages), st>>>(dz128, wT, x0, x1, p, f);
   return after_launch("dgradT_fused_kernel");
 }
 
@@ -622,7 +748,7 @@ int launch_wgrad(const Ctx& cx, const CUtensorMap& a, const CUtensorMap& b0, con
   const int grid = groups * p.n_blocks * p.splits;
   if (gate != nullptr) {
     if (grid > kBiasRowsMax / 16) return fail(CLSTM_EINVAL, "wgrad + gate workers: grid %d too large", grid);
-    if (cx.knobs.wg_gate == 2)  // register-rebalanced workers
+    if (cx.knobs.wg_gate == 2 || (cx.knobs.wg_gate == 0 && cx.knobs.hybrid_wg == 2))  // register-rebalanced workers
       wgrad_kernel<E, 2><<<grid, kWgThreads + kWgGateThreads2, smem, st>>>(a, b0, b1, p, *gate);
     else
       wgrad_kernel<E, 1><<<grid, kWgThreads + kWgGateThreads, smem, st>>>(a, b0, b1, p, *gate);
@@ -751,7 +877,7 @@ inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
 // A source equal to cs.dxb is the dx this launch produces: it is consumed from shared memory and never written.
 template <typename E>
 int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const float* own, const float* e1,
-                     const float* e2, int buf, cudaStream_t st) {
+                     const float* e2, int buf, cudaStream_t st, int fuse_units = 0x7fffffff) {
   const size_t npix = ctx.geo.npix();
   const int HP = ctx.HP;
   GateFuse f;
@@ -772,9 +898,10 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
   f.bias_partial = cn.bpart;
   f.dz_absmax = ctx.amax + 1;
   f.HP = HP;
+  f.fuse_units = fuse_units;
   f.pf_dist = ctx.knobs.fuse_pf;
-  return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.m_dhT, ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0},
-                                ctx.geo, ctx.geo.B, f, st);
+  return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT,
+                                ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0}, ctx.geo, ctx.geo.B, f, st);
 }
 
 // Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
@@ -889,6 +1016,9 @@ struct clstm_plan {
   void* psteps = nullptr;
   unsigned int* pcounter = nullptr;
   PersistParams pparams;
+  // CUDA-graph replay of the forward / backward launch sequences (launch-bound shapes only)
+  bool graph_ok = false;
+  GraphCache g_fwd, g_bwd;
 };
 
 namespace {
@@ -1335,8 +1465,18 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       }
     }
   } else if (fuse) {
+    // hybrid split (see below): only when a unit is 256 CONSECUTIVE pixels (one-row 128-pixel tiles, W a multiple
+    // of 256), so that "units >= hybrid_units" is the pixel range [256 * hybrid_units, npix)
+    int hybrid_units = 0;
+    if (ctx.knobs.hybrid_pct > 0 && ctx.knobs.hybrid_pct < 100 && geo.BW == 128 && geo.BH == 1 && geo.W % 256 == 0) {
+      const long long units = static_cast<long long>(npix / 256);
+      hybrid_units = static_cast<int>(units * ctx.knobs.hybrid_pct / 100);
+      if (hybrid_units < 1 || hybrid_units >= units) hybrid_units = 0;
+    }
+    if (hybrid_units > 0) bias_rows = kBiasRowsMax;
     for (int k = 0; k < ncell; ++k)
-      CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0, static_cast<size_t>(kGateGradBlocks) * 4 * HP * 4, st));
+      CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0,
+                             static_cast<size_t>(hybrid_units > 0 ? kBiasRowsMax : kGateGradBlocks) * 4 * HP * 4, st));
     int b = 0;
     bool gate_done = false;  // gate gradient of ops[n] already computed into dz[b] by the previous dgrad
     for (size_t n = 0; n < ops.size(); ++n) {
@@ -1355,18 +1495,40 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       }
       gate_done = false;
       bool fused_here = false;
+      WgGateWork gw;
+      const WgGateWork* gwp = nullptr;
       if (n + 1 < ops.size() && (!cs.with_x || cs.g.CIP == 64)) {
         const BackOp& nx = ops[n + 1];
         CellState& cn = p->cells[nx.k];
         if (nx.k != o.k) {
           if (nx.head) RC_TRY(head_back(nx.t));  // dstack must be ready; nothing in flight still reads it
-          RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, (nx.t == cn.T - 1) ? nullptr : cn.dh_own, nx.e1, nx.e2, b, st));
+          const float* own_n = (nx.t == cn.T - 1) ? nullptr : cn.dh_own;
+          int fuse_units = 0x7fffffff;
+          if (hybrid_units > 0 && cs.with_x) {
+            // hybrid: the first hybrid_units units (256 consecutive pixels each) finish their gate gradient in this
+            // dgrad's epilogue, the remaining pixels on the worker warps of the wgrad launch below (they read dx,
+            // which the dgrad then writes for those units only).  Spreads the HBM-bound pointwise pass over BOTH GEMMs.
+            fuse_units = hybrid_units;
+            memset(&gw, 0, sizeof(gw));
+            gw.gates = static_cast<const E*>(cn.gates) + static_cast<size_t>(nx.t) * npix * 4 * HP;
+            gw.c_prev = (nx.t == 0) ? nullptr : cn.c + static_cast<size_t>(cslot(cn, nx.t)) * npix * HP;
+            gw.c_next = cn.c + static_cast<size_t>(cslot(cn, nx.t + 1)) * npix * HP;
+            gw.src0 = own_n, gw.src1 = nx.e1, gw.src2 = nx.e2;
+            gw.dc = cn.dc;
+            gw.dz_out = ctx.dzb[b ^ 1];
+            gw.bias_partial = cn.bpart;
+            gw.dz_absmax = ctx.amax + 1;
+            gw.npix = static_cast<unsigned>(npix);
+            gw.pix_begin = static_cast<unsigned>(hybrid_units) * 256u;
+            gwp = &gw;
+          }
+          RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nx.e1, nx.e2, b, st, fuse_units));
           fused_here = true;
           gate_done = true;
         }
       }
       if (!fused_here) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
-      RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b));
+      RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b, gwp));
       if (fused_here) b ^= 1;
     }
   } else {
@@ -1750,6 +1912,10 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
 }
 
 int clstm_plan_destroy(clstm_plan_t* plan) {
+  if (plan) {
+    plan->g_fwd.clear();
+    plan->g_bwd.clear();
+  }
   if (plan && plan->ctx.side) {
     cudaStreamSynchronize(plan->ctx.side);
     for (int i = 0; i < 2; ++i) {
@@ -1817,6 +1983,11 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
   RC_TRY(persist_setup(p, st));
+  // launch-bound when a cell step is at most a couple of waves of tiles; the side-stream schedule is not captured
+  p->g_fwd.clear();
+  p->g_bwd.clear();
+  p->graph_ok = ctx.knobs.graph && !ctx.knobs.overlap &&
+                static_cast<long long>(g.B) * g.tiles_w * g.tiles_h * (ctx.HP / 64) <= 4ll * ctx.dev.sms;
   p->bound = true;
   p->weights_set = false;
   p->forward_done = false;
@@ -1848,9 +2019,12 @@ int clstm_rollout_forward_layout(clstm_plan_t* p, const float* x, int x_layout, 
   if (!p->bound || !p->weights_set) return fail(CLSTM_ESTATE, "forward before bind / set_weights");
   if (x_layout != CLSTM_X_BTCHW && x_layout != CLSTM_X_BTHWC) return fail(CLSTM_EINVAL, "unknown x layout %d", x_layout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL_(E) plan_forward<E>(p, x, y, st, x_layout == CLSTM_X_BTHWC)
-  return DISPATCH_E(p->cfg.dtype, CALL_);
+  return run_graphed(p->g_fwd, p->graph_ok, {x, y, reinterpret_cast<const void*>(static_cast<uintptr_t>(x_layout))}, st,
+                     [&](cudaStream_t s) -> int {
+#define CALL_(E) plan_forward<E>(p, x, y, s, x_layout == CLSTM_X_BTHWC)
+                       return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
+                     });
 }
 
 int clstm_rollout_backward(clstm_plan_t* p, const float* dy, const float* y, float* const* grads, int n_grads,
@@ -1862,9 +2036,13 @@ int clstm_rollout_backward(clstm_plan_t* p, const float* dy, const float* y, flo
   if (n_grads != 2 * p->ncell + 2)
     return fail(CLSTM_EINVAL, "expected %d gradient tensors, got %d", 2 * p->ncell + 2, n_grads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL_(E) plan_backward<E>(p, dy, y, grads, accumulate, st)
-  return DISPATCH_E(p->cfg.dtype, CALL_);
+  std::vector<const void*> key = {dy, y, reinterpret_cast<const void*>(static_cast<uintptr_t>(accumulate != 0))};
+  for (int i = 0; i < n_grads; ++i) key.push_back(grads[i]);
+  return run_graphed(p->g_bwd, p->graph_ok, std::move(key), st, [&](cudaStream_t s) -> int {
+#define CALL_(E) plan_backward<E>(p, dy, y, grads, accumulate, s)
+    return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
+  });
 }
 
 int clstm_plan_grad_status(clstm_plan_t* p, float* out4, void* stream) {
@@ -1872,6 +2050,17 @@ int clstm_plan_grad_status(clstm_plan_t* p, float* out4, void* stream) {
   if (!p->bound || !p->cfg.training) return fail(CLSTM_ESTATE, "grad_status needs a bound training plan");
   grad_status_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(p->ctx.scale, p->ctx.amax, out4);
   return after_launch("grad_status_kernel");
+}
+
+int clstm_plan_info(const clstm_plan_t* p, int what, long long* out) {
+  if (!p || !out) return fail(CLSTM_EINVAL, "null argument");
+  switch (what) {
+    case CLSTM_INFO_PERSISTENT_CHAIN: *out = p->persist_ok ? 1 : 0; return 0;
+    case CLSTM_INFO_GRAPH_ENABLED: *out = (p->graph_ok && !p->g_fwd.disabled && !p->g_bwd.disabled) ? 1 : 0; return 0;
+    case CLSTM_INFO_GRAPH_CAPTURES: *out = static_cast<long long>(p->g_fwd.captures + p->g_bwd.captures); return 0;
+    case CLSTM_INFO_GRAPH_REPLAYS: *out = static_cast<long long>(p->g_fwd.replays + p->g_bwd.replays); return 0;
+    default: return fail(CLSTM_EINVAL, "unknown info item %d", what);
+  }
 }
 
 int clstm_plan_read_state(clstm_plan_t* p, int cell, int step, float* h_out, float* c_out, void* stream) {

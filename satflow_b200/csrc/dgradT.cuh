@@ -250,6 +250,9 @@ struct GateFuse {
   float* bias_partial;   // [gridDim.x][4*HP], accumulated
   unsigned int* dz_absmax;  // range statistics of the 16-bit dz this pass writes (float bits, see fold_absmax)
   int HP;
+  int fuse_units;        // hybrid schedule: only units < fuse_units run the gate gradient here; for the others the dx
+                         // block is written to HBM (tmX0) and the worker warps of the following wgrad launch finish
+                         // the job (clstm.cu "hybrid").  INT_MAX = everything here.
 };
 
 inline size_t dgradTf_smem_bytes(int stages) {
@@ -259,10 +262,16 @@ inline size_t dgradTf_smem_bytes(int stages) {
 // TEAMS = epilogue teams of 4 warps (one warp per TMEM lane quadrant); a team owns 256/TEAMS accumulator columns.
 // TEAMS = 2: 384 threads, 32-pixel groups, two register sets of loads in flight per thread.
 // TEAMS = 4: 640 threads (<= 96 registers), 16-pixel groups, one set per thread — twice the warps per scheduler.
-template <typename E, int TEAMS>
+// SETS (TEAMS == 2 only) = register sets of raw gate-gradient loads a thread keeps in flight.  The pass is latency
+// bound (ncu source view, profiles/r2_fused_dgrad_ncu.md: a third of all warp samples sit on the first use of a
+// loaded value), and registers are what holds loads in flight.  SETS = 4 rebalances them with setmaxnreg — the four
+// control warps need 56 registers, not the 168 of the launch bound: 128 x 112 registers move to the 256 epilogue
+// threads (224 each) — and every item's loads are then issued a WHOLE 32-pixel group ahead of their use.
+template <typename E, int TEAMS, int SETS = 2>
 __global__ void __launch_bounds__(128 + TEAMS * 128, 1)
 dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmX1, const DgradTParams p, const GateFuse f) {
+                    const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                    const DgradTParams p, const GateFuse f) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_stg = smem + p.stages * kDtStageBytes;
@@ -307,6 +316,9 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
     b = mt / (p.tiles_w * p.tiles_h);
   };
 
+  if (warp < 4) {
+  // ---- control warpgroup (TMA producer, MMA issuer, TMEM allocator, idle): gives registers back when SETS == 4
+  if constexpr (SETS == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == 0) {
     if (lane < 3) {
       int stage = 0;
@@ -373,7 +385,9 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if constexpr (SETS == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
     // ===================== epilogue: transpose 32-pixel groups, h-part -> TMA store, x-part -> fused gate-grad ======
     // The gate-gradient part is latency bound unless its global loads are kept in flight while the thread drains
     // TMEM and waits at barriers: items are 1 pixel x 4 channels (32 registers of raw loads), two register sets
@@ -411,7 +425,7 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
     };
     auto tile_base = [&](int unit) -> TileBase {
       TileBase t{0u, 0, 0};
-      if (unit >= total_units) return t;
+      if (unit >= total_units || unit >= f.fuse_units) return t;  // no gate-gradient items for this unit
       int w0, h0, b;
       tile_origin(unit, half, w0, h0, b);
       if (b >= p.B) return t;
@@ -487,9 +501,13 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
     };
 
     TileBase tb_cur = tile_base(blockIdx.x), tb_next;
-    Raw ra, rb;
+    Raw ra, rb, rc, rd;
     issue(ra, tb_cur, 0, 0);
     if (TEAMS == 2) issue(rb, tb_cur, 0, 1);
+    if (TEAMS == 2 && SETS == 4) {
+      issue(rc, tb_cur, 0, 2);
+      issue(rd, tb_cur, 0, 3);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -505,7 +523,7 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
           uint32_t v[GP];
 #pragma unroll
           for (int i = 0; i < GP / 16; ++i) tmem_ld16(taddr + g * GP + i * 16, *reinterpret_cast<uint32_t(*)[16]>(v + i * 16));
-          if (q == 0 && lane == 1) tma_store_wait_read();
+          if (q == 0 && lane < 2) tma_store_wait_read();
           named_bar_sync(bar_id, 128);  // staging free: the previous group's TMA store and fused reads are done
           tmem_ld_wait();
           if (g == 3) {
@@ -528,11 +546,30 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
           }
           tma_store_commit();
         }
+        if (q == 0 && lane == 0 && unit >= f.fuse_units && f.h_block == 1) {
+          // hybrid schedule: the gate gradient of these pixels runs in the next wgrad launch, which reads dx from HBM
+#pragma unroll
+          for (int s2 = 0; s2 < GP / 16; ++s2) {
+            const int px = pcol0 + g * GP + s2 * 16;
+            tma_store_4d(&tmX0, stg + s2 * 16 * 64, 0, w0 + (px & (p.BW - 1)), h0 + (px >> p.lbw), b);
+          }
+          tma_store_commit();
+        }
         // fused gate gradient of the consumer cell: passes of 8 pixels, loads issued ahead of their use
         const int ng = (g + 1) & 3;
         const TileBase& tbn = (g == 3) ? tb_next : tb_cur;
-        if (f.pf_dist) prefetch_group(tbn, ng);
-        if (TEAMS == 2) {
+        if (f.pf_dist && SETS != 4) prefetch_group(tbn, ng);
+        if (TEAMS == 2 && SETS == 4) {
+          // every set is re-issued for the NEXT group right after its item of this group is consumed
+          consume(ra, 0);
+          issue(ra, tbn, ng, 0);
+          consume(rb, 1);
+          issue(rb, tbn, ng, 1);
+          consume(rc, 2);
+          issue(rc, tbn, ng, 2);
+          consume(rd, 3);
+          issue(rd, tbn, ng, 3);
+        } else if (TEAMS == 2) {
           consume(ra, 0);
           issue(ra, tb_cur, g, 2);
           consume(rb, 1);
@@ -552,7 +589,7 @@ dgradT_fused_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (q == 0 && lane == 1) tma_store_wait_all();
+    if (q == 0 && lane < 2) tma_store_wait_all();
     fold_absmax<E>(zmax, f.dz_absmax);
     // bias partial sums: reduce over the 16 threads (both halves) that share a channel chunk, one gate at a time
     const int te = threadIdx.x - 128;  // over the epilogue warps; te & 15 == chunk

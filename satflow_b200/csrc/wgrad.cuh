@@ -65,6 +65,7 @@ struct WgGateWork {
   float* bias_partial;   // [gridDim.x * 16][4*HP]: one row per worker warp, accumulated
   unsigned int* dz_absmax;  // range statistics of the dz written here (float bits, see fold_absmax)
   unsigned npix;         // HP == 64 and npix * 256 < 2^32 (checked on the host)
+  unsigned pix_begin;    // the workers handle pixels [pix_begin, npix) (hybrid schedule: the rest ran in the dgrad epilogue)
 };
 
 // GATE: 0 = plain wgrad (256 threads); 1 = + 16 gate-gradient worker warps, one item in flight per worker (validated,
@@ -170,7 +171,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int a = 0; a < 4; ++a) *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) = dzp[a];
     };
     const unsigned stride = gridDim.x * 24u;  // 384 workers = 24 pixels per CTA pass
-    unsigned p0 = blockIdx.x * 24u + plane, p1 = p0 + stride;
+    unsigned p0 = gw.pix_begin + blockIdx.x * 24u + plane, p1 = p0 + stride;
     Raw ra, rb;
     issue(ra, p0);
     issue(rb, p1);
@@ -317,7 +318,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
       for (int e = 0; e < 4; ++e) bsum[a][e] = 0.f;
     uint32_t zmax = 0;
-    for (unsigned pix = blockIdx.x * 32u + plane; pix < gw.npix; pix += gridDim.x * 32u) {
+    for (unsigned pix = gw.pix_begin + blockIdx.x * 32u + plane; pix < gw.npix; pix += gridDim.x * 32u) {
       const unsigned o4 = pix * 256u + 0u, o1 = pix * 64u + chunk * 4;
       uint2 g[4];
 #pragma unroll

@@ -209,6 +209,14 @@ class RolloutPlan:
                 self._capture_grad_status()
         self.pending_backward = False
 
+    INFO = {"persistent_chain": 0, "graph_enabled": 1, "graph_captures": 2, "graph_replays": 3}
+
+    def info(self, what: str) -> int:
+        """include/clstm.h clstm_plan_info: how this plan executes (persistent forward chain, CUDA-graph replay)."""
+        out = ctypes.c_longlong(0)
+        _lib.check(_lib.lib().clstm_plan_info(self._h, self.INFO[what], ctypes.byref(out)))
+        return int(out.value)
+
     KERNELS = {"cell_fwd": 0, "gate_grad": 1, "dgrad": 2, "wgrad": 3, "wgrad+gate_grad": 4, "dgrad_fused": 5}
 
     def profile_kernel(self, kind: str, cell: int, step: int) -> None:
