@@ -122,8 +122,10 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_median": statistics.median(pw) if pw else None,
+                "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -531,8 +533,10 @@ def run_ours(args):
         tensor_kernels = {
             "cell_step": ("convgemm_kernel<EPI_LSTM>: fused conv + LSTM cell step (training variant, also writes gates)",
                           "convgemm_kernel<__half, 0>"),
+            "dgradT_fused2_kernel": ("dgradT_fused2_kernel: data gradient + gate gradient of the next chain step on "
+                                     "dedicated worker warps", "dgradT_fused"),
             "dgradT_fused_kernel": ("dgradT_fused_kernel: data gradient + fused gate gradient of the next chain step",
-                                    "dgradT_fused_kernel"),
+                                    "dgradT_fused"),
             "wgrad[halo rows]": ("wgrad_kernel (halo rows): weight gradient", "wgrad_kernel"),
             "wgrad_gate_kernel": ("wgrad_kernel + gate-gradient worker warps", "wgrad_kernel"),
             "dgradT_kernel": ("dgradT_kernel: data gradient", "dgradT_kernel"),

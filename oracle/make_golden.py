@@ -49,6 +49,21 @@ def main() -> None:
             out["grad." + k] = v.grad.numpy()
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
         print(name, "loss", loss.item(), {k: v.shape for k, v in out.items() if k.startswith("grad.")})
+    # A checkpoint in the format Lightning's ModelCheckpoint(save_weights_only=True) writes for this module
+    # (configs/callbacks/default.yaml:1-17): `state_dict` + the `hyper_parameters` of save_hyperparameters()
+    # (conv_lstm.py:33), produced by the reference class itself, plus one seeded input and the reference's output for it.
+    torch.manual_seed(11)
+    hp = dict(hidden_dim=16, input_channels=12, out_channels=3, forecast_steps=5, lr=1e-4, visualize=False, loss="mse",
+              pretrained=False, conv_type="standard")
+    lit = Lit(**hp)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(2, 3, 12, 10, 12, generator=g)
+    with torch.no_grad():
+        y = lit(x, hp["forecast_steps"])
+    torch.save({"epoch": 3, "global_step": 1234, "pytorch-lightning_version": "1.4.9",
+                "state_dict": {k: v.clone() for k, v in lit.state_dict().items()}, "hyper_parameters": hp,
+                "golden": {"x": x, "y": y}}, os.path.join(GOLDEN_DIR, "lightning_best.ckpt"))
+    print("lightning_best.ckpt ok")
     for name, (B, cin, hid, H, W, kh, kw) in CELL_CASES.items():
         torch.manual_seed(7)
         cell = Cell(cin, hid, (kh, kw), True)

@@ -264,9 +264,31 @@ class EncoderDecoderConvLSTM(_Base):
         """Load a reference Lightning checkpoint (path or dict): ``state_dict`` has the keys of SURVEY.md §8(b);
         ``hyper_parameters`` (from save_hyperparameters, conv_lstm.py:33) are returned for inspection."""
         if not isinstance(ckpt, dict):
-            ckpt = torch.load(ckpt, map_location="cpu")
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
         self.load_state_dict(ckpt.get("state_dict", ckpt), strict=strict)
         return ckpt.get("hyper_parameters", {})
+
+    def lightning_checkpoint(self, epoch: int = 0, global_step: int = 0) -> dict:
+        """The dict Lightning's ModelCheckpoint(save_weights_only=True) writes for this module
+        (configs/callbacks/default.yaml:1-17): reference state_dict keys + ``hyper_parameters``.  ``torch.save`` it
+        and the reference class loads it (``load_state_dict(ckpt["state_dict"])`` strict, or ``load_from_checkpoint``)."""
+        return {"epoch": epoch, "global_step": global_step, "pytorch-lightning_version": "1.4.9",
+                "state_dict": {k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
+                "hyper_parameters": dict(self.hparams)}
+
+    @classmethod
+    def load_from_checkpoint(cls, ckpt, map_location=None, strict: bool = True, **overrides):
+        """Lightning's ``LightningModule.load_from_checkpoint`` for this class: construct from the checkpoint's
+        ``hyper_parameters`` (keyword overrides win) and load its ``state_dict``."""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location=map_location or "cpu", weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        names = ("hidden_dim", "input_channels", "out_channels", "forecast_steps", "lr", "visualize", "loss", "pretrained",
+                 "conv_type")
+        model = cls(**{k: v for k, v in hp.items() if k in names})
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        return model
 
     def forward(self, x, future_seq=0, hidden_state=None):
         return self.model.forward(x, future_seq, hidden_state)

@@ -160,3 +160,47 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_lightning_format_checkpoint_round_trip(tmp_path):
+    """tests/golden/lightning_best.ckpt was written by the REFERENCE class in the format Lightning's
+    ModelCheckpoint(save_weights_only=True) uses (state_dict + hyper_parameters of save_hyperparameters,
+    conv_lstm.py:33).  load_from_checkpoint rebuilds the module from it; lightning_checkpoint() writes the same format
+    back, bit for bit."""
+    path = os.path.join(ROOT, "tests", "golden", "lightning_best.ckpt")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    m = S.EncoderDecoderConvLSTM.load_from_checkpoint(path)
+    hp = ck["hyper_parameters"]
+    assert (m.model.hidden_dim, m.model.input_channels, m.model.out_channels, m.forecast_steps, m.lr) == (
+        hp["hidden_dim"], hp["input_channels"], hp["out_channels"], hp["forecast_steps"], hp["lr"])
+    assert dict(m.hparams) == hp
+    for k, v in ck["state_dict"].items():
+        assert torch.equal(m.state_dict()[k], v), k
+    out = tmp_path / "resaved.ckpt"
+    torch.save(m.lightning_checkpoint(epoch=ck["epoch"], global_step=ck["global_step"]), out)
+    ck2 = torch.load(out, map_location="cpu", weights_only=False)
+    assert list(ck2["state_dict"].keys()) == list(ck["state_dict"].keys())
+    assert all(torch.equal(ck2["state_dict"][k], ck["state_dict"][k]) for k in ck["state_dict"])
+    assert ck2["hyper_parameters"] == hp and ck2["epoch"] == 3 and ck2["global_step"] == 1234
+    # keyword overrides win over the stored hyper-parameters, like Lightning's load_from_checkpoint(**kwargs)
+    assert S.EncoderDecoderConvLSTM.load_from_checkpoint(path, forecast_steps=2).forecast_steps == 2
+
+
+@pytest.mark.reference
+def test_reference_class_loads_a_checkpoint_written_here(tmp_path):
+    """The other direction: a checkpoint written by this package loads strictly into the unmodified reference class and
+    reproduces the output stored in the fixture bit for bit (CPU, build container only)."""
+    from oracle.reference_loader import load_reference
+
+    path = os.path.join(ROOT, "tests", "golden", "lightning_best.ckpt")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ours = S.EncoderDecoderConvLSTM.load_from_checkpoint(path)
+    out = tmp_path / "from_b200.ckpt"
+    torch.save(ours.lightning_checkpoint(), out)
+    ck2 = torch.load(out, map_location="cpu", weights_only=False)
+    _, _, Lit = load_reference()
+    ref = Lit(**ck2["hyper_parameters"])
+    ref.load_state_dict(ck2["state_dict"])  # strict
+    with torch.no_grad():
+        y = ref(ck["golden"]["x"], ck2["hyper_parameters"]["forecast_steps"])
+    assert torch.equal(y, ck["golden"]["y"])

@@ -14,7 +14,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --c
 python tools/launch_summary.py gpurun_out/${R}_launches_train_step.csv > gpurun_out/${R}_launches_train_step_summary.txt 2>/dev/null
 head -12 gpurun_out/${R}_launches_train_step_summary.txt
 i=0
-for spec in "convgemm_kernel:30:1" "dgradT_fused_kernel:30:1" "wgrad_kernel:30:2" "head_rows_kernel:0:1" "gate_grad_kernel:0:1"; do
+for spec in "convgemm_kernel:30:1" "dgradT_fused:30:1" "wgrad_kernel:30:2" "head_rows_kernel:0:1" "gate_grad_kernel:0:1"; do
   i=$((i+1))
   k=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; cnt=${rest#*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c $cnt \

@@ -11,3 +11,18 @@ r = G.rollout_case(1, 1, 2, 12, 8, 12, 34, 300, states=False)  # head strips + r
 print("W300", max(r.values()))
 r = G.cell_case(1, 12, 32, 6, 40, 3, 3)
 print("cell", max(r.values()))
+# round 2: the persistent forward chain + CUDA-graph replay run on all of the above (every shape fits 148 CTAs);
+# the per-step kernels, both fused-dgrad generations and the native cell stepper on a second pass
+import torch
+from satflow_b200 import ConvLSTMCell
+for env in ({"CLSTM_PERSIST": "0", "CLSTM_GRAPH": "0"}, {"CLSTM_FUSE_WORKERS": "0"}, {"CLSTM_HYBRID": "50"}):
+    os.environ.update(env)
+    r = G.rollout_case(1, 2, 3, 12, 64, 5, 4, 256, states=False)
+    print(env, max(r.values()))
+    for k in env:
+        del os.environ[k]
+r = G.cell_unrolled_case(1, 12, 16, 6, 20, 3)
+print("unrolled cell", max(r.values()))
+cell = ConvLSTMCell(12, 32, (3, 3), True).cuda()
+st = cell.native(1, (6, 40)).step(torch.randn(1, 12, 6, 40, device="cuda")).step()
+print("native", float(st.state()[0].abs().max()))
