@@ -513,6 +513,17 @@ def run_ours(args):
                           "tflops": algorithmic_flops_fwd(B, t_in, t_out, C, hid, Co, HW, HW) / ms_inf / 1e9,
                           "config": "BASELINE configs[1]: fwd only, batch 16 per GPU"}
 
+    if world == 1 and not args.no_extras and args.dtype == "fp16":
+        # informational: the same inference rollout with bf16 operands (opt-in; outputs within 2e-3, recurrent states not —
+        # DESIGN.md §2).  Faster under the power cap: fewer multiplier bits toggle.
+        prev = model.model.operand_dtype
+        model.model.operand_dtype = "bf16"
+        for _ in range(3):
+            infer()
+        ms_b, _ = timed(infer, args.steps)
+        model.model.operand_dtype = prev
+        extra["inference"]["bf16_operands"] = {"frames_per_s": B * (t_in + t_out) / ms_b * 1e3, "ms_per_step": ms_b}
+
     peaks = measured_peaks()
     roof = None
     cpu = None
@@ -530,31 +541,52 @@ def run_ours(args):
         fl = cell_step_flops(B, hid, hid, HW, HW)  # a cell step with a 64-channel input: K = (64 + 64) * 9
         npix = B * HW * HW
         gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
+        # algorithmic bytes per launch (16-bit x / h / gates / dz, fp32 c / dc / dh; weights negligible)
+        px = npix * hid
+        by_cell = px * (2 + 2 + 4 + 2 + 4 + 8)            # x, h_prev, c_prev read; h, c, 4 gates written
+        by_fused = px * (8 + 4 + 8 + 4 + 4 + 4 + 8 + 8)    # dz read, dh_prev written; gates, c_prev, c_next, ONE dh source from HBM
+                                                           # (the other is this launch's dx, in shared memory), dc r/w, dz written
+        by_wgrad = px * (8 + 2 + 2)                        # dz, x, h_prev read
+        by_dgrad = px * (8 + 4 + 4)                        # dz read, dx and dh_prev written
         tensor_kernels = {
             "cell_step": ("convgemm_kernel<EPI_LSTM>: fused conv + LSTM cell step (training variant, also writes gates)",
-                          "convgemm_kernel<__half, 0>"),
+                          "convgemm_kernel<__half, 0>", by_cell),
             "dgradT_fused2_kernel": ("dgradT_fused2_kernel: data gradient + gate gradient of the next chain step on "
-                                     "dedicated worker warps", "dgradT_fused"),
+                                     "dedicated worker warps", "dgradT_fused", by_fused),
             "dgradT_fused_kernel": ("dgradT_fused_kernel: data gradient + fused gate gradient of the next chain step",
-                                    "dgradT_fused"),
-            "wgrad[halo rows]": ("wgrad_kernel (halo rows): weight gradient", "wgrad_kernel"),
-            "wgrad_gate_kernel": ("wgrad_kernel + gate-gradient worker warps", "wgrad_kernel"),
-            "dgradT_kernel": ("dgradT_kernel: data gradient", "dgradT_kernel"),
+                                    "dgradT_fused", by_fused),
+            "wgrad[halo rows]": ("wgrad_kernel (halo rows): weight gradient", "wgrad_kernel", by_wgrad),
+            "wgrad_gate_kernel": ("wgrad_kernel + gate-gradient worker warps", "wgrad_kernel", by_wgrad + gg_bytes),
+            "dgradT_kernel": ("dgradT_kernel: data gradient", "dgradT_kernel", by_dgrad),
         }
         in_situ = []
-        for key, (label, ncu_name) in tensor_kernels.items():
+        for key, (label, ncu_name, nbytes) in tensor_kernels.items():
             if key not in tr:
                 continue
             n, tot_ms, avg_us = tr[key]
-            ach = fl / (avg_us * 1e-6) / 1e12
+            sec = avg_us * 1e-6
+            t_tensor = fl / (peaks["bf16_sustained"] * 1e12)   # roofline times of this launch on either resource
+            t_hbm = nbytes / (peaks["hbm"] * 1e9)
             traffic, tsrc = ncu_traffic(ncu_name)
-            in_situ.append({"kernel": label, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"],
-                            "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
-                            "traffic_source": tsrc, "launch_ms": avg_us * 1e-3, "launches_per_step": n // 2,
-                            "share_of_step_ms": tot_ms / 2, "flops_per_launch": fl,
-                            "peak_source": peaks["source"] + " sustained: kernel timed inside the training step",
-                            "timing": "CUDA event after every launch of 2 training steps on the launching stream "
-                                      "(clstm_trace_enable), taken right after the timed region"})
+            common = {"kernel": label, "traffic": traffic, "traffic_source": tsrc, "launch_ms": avg_us * 1e-3,
+                      "launches_per_step": n // 2, "share_of_step_ms": tot_ms / 2, "flops_per_launch": fl,
+                      "bytes_per_launch": nbytes,
+                      "tensor": {"achieved": fl / sec / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                                 "frac": t_tensor / sec},
+                      "hbm": {"achieved": nbytes / sec / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": t_hbm / sec},
+                      "peak_source": peaks["source"] + "; tensor: sustained figure (kernel timed inside the training "
+                                     "step), hbm: the copy bandwidth",
+                      "timing": "CUDA event after every launch of 2 training steps on the launching stream "
+                                "(clstm_trace_enable), taken right after the timed region"}
+            # the binding resource is the one whose roofline time for this launch is longer (arithmetic intensity
+            # against the ridge point): the fused dgrad carries 3.2 GB for 0.62 TFLOP = 191 FLOP/B < 212
+            if t_hbm > t_tensor:
+                common.update({"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                               "frac": t_hbm / sec})
+            else:
+                common.update({"bound": "tensor", "achieved": fl / sec / 1e12, "peak": peaks["bf16_sustained"],
+                               "unit": "TFLOP/s", "frac": t_tensor / sec})
+            in_situ.append(common)
         if "gate_grad_kernel" in tr:
             n, tot_ms, avg_us = tr["gate_grad_kernel"]
             in_situ.append({"kernel": "gate_grad_kernel (pointwise gate gradient, standalone launches)", "bound": "hbm",
