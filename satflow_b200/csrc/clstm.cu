@@ -962,8 +962,8 @@ int cell_finalize(const Ctx& ctx, CellState& cs, float* dw, float* db, int accum
     RC_TRY(after_launch("cell_wgrad_finalize_kernel"));
   }
   if (db) {
-    cell_bias_finalize_kernel<<<(4 * g.hid + 255) / 256, 256, 0, st>>>(cs.bpart, db, bias_rows, g.hid,
-                                                                       ctx.HP, ctx.scale + 1, accumulate);
+    cell_bias_finalize_kernel<<<(4 * g.hid + 31) / 32, 256, 0, st>>>(cs.bpart, db, bias_rows, g.hid,
+                                                                     ctx.HP, ctx.scale + 1, accumulate);
     RC_TRY(after_launch("cell_bias_finalize_kernel"));
   }
   return 0;

@@ -634,16 +634,30 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __r
 }
 
 // Cell bias gradient: db_ref[gate*hid + j] = scale * sum_blocks partial[blk][gate*HP + j]
-__global__ void cell_bias_finalize_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks,
-                                          int hid, int HP, const float* __restrict__ scale_ptr, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 4 * hid) return;
-  const float scale = *scale_ptr;
-  const int gate = i / hid, j = i % hid;
+// One block reduces 32 output columns: 8 row lanes per column walk the partial rows with stride 8 (coalesced 128-byte
+// row segments), then a fixed-order tree over the lanes in shared memory — deterministic, and ~6x shorter than one
+// thread per column walking all rows (which cost 51 us per cell on launch-bound shapes).
+__global__ void __launch_bounds__(256)
+cell_bias_finalize_kernel(const float* __restrict__ partial, float* __restrict__ db, int nblocks, int hid, int HP,
+                          const float* __restrict__ scale_ptr, int accumulate) {
+  __shared__ float red[8][33];
+  const int col = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + col;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * 4 * HP + gate * HP + j];
-  s *= scale;
-  db[i] = accumulate ? db[i] + s : s;
+  if (i < 4 * hid) {
+    const int gate = i / hid, j = i % hid;
+    const float* src = partial + gate * HP + j;
+    for (int b = lane; b < nblocks; b += 8) s += src[static_cast<size_t>(b) * 4 * HP];
+  }
+  red[lane][col] = s;
+  __syncthreads();
+  if (lane == 0 && i < 4 * hid) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][col];
+    t *= *scale_ptr;
+    db[i] = accumulate ? db[i] + t : t;
+  }
 }
 
 // Cell weight gradient: dW_ref[n_ref][c_full][tap] = scale * sum_splits D[s][gate*HP + j][k(c_full,tap)]
