@@ -125,8 +125,10 @@ class ConvLSTMCell(nn.Module):
         key = (B, C, H, W, self.operand_dtype, x.device.index)
         plan = self._plans.get(key)
         if plan is None:
-            if len(self._plans) >= 2:  # bounded: each plan pins a workspace
-                self._plans.pop(next(iter(self._plans))).close()
+            if len(self._plans) >= 2:
+                # bounded: each plan pins a scratch workspace.  The evicted plan is only dropped, not closed: an autograd
+                # node of an earlier forward may still hold it (it is destroyed when the last reference goes away)
+                self._plans.pop(next(iter(self._plans)))
             plan = CellPlan(B, H, W, C, self.hidden_dim, tuple(self.kernel_size), self.operand_dtype, x.device)
             self._plans[key] = plan
         return plan
