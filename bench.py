@@ -481,23 +481,39 @@ def run_ours(args):
     # step i, as a DataLoader with pin_memory does) and the loss is read back to the host every step.
     from satflow_b200.prefetch import DevicePrefetcher
 
-    def e2e_run(steps):
-        pf = DevicePrefetcher(((x_host, y_host) for _ in range(steps)), dev)
-        out = 0.0
-        for xd, td in pf:
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    n_e2e_warm = 2
+    # ONE loader pipeline across warm-up and timed steps (steady state): while step i runs, the copy of step i + 1's
+    # inputs is in flight.  The timed region therefore holds exactly one H2D copy per timed step (those of steps
+    # 1 .. K and of one spare batch that keeps the pipeline full), and every step's loss is read on the host — one step
+    # late, from a pinned two-slot ring guarded by events — so the host stays one step ahead of the device, as a
+    # training loop that logs its loss does.
+    pf = iter(DevicePrefetcher(((x_host, y_host) for _ in range(n_e2e_warm + args.steps + 1)), dev))
+    losses = []
+
+    def e2e_steps(n, i0):
+        for i in range(i0, i0 + n):
+            xd, td = next(pf)
             loss = train_step(xd, td)
             pf.done_with_current()
-            out = loss.item()
-        return out
+            loss_host[i & 1].copy_(loss.detach(), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > i0:
+                loss_ev[(i - 1) & 1].synchronize()
+                losses.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(i0 + n - 1) & 1].synchronize()
+        losses.append(float(loss_host[(i0 + n - 1) & 1]))
 
-    e2e_run(2)
+    e2e_steps(n_e2e_warm, 0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_run(args.steps)
+    e2e_steps(args.steps, n_e2e_warm)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    assert len(losses) == n_e2e_warm + args.steps and all(v == v for v in losses)
 
     # inference (BASELINE configs[1]): forward rollout only, same shapes
     extra = {}
@@ -655,8 +671,15 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
             "config": workload_config(world, args.global_batch),
             "e2e": {"value": frames / ms_e2e * 1e3, "unit": "frames/s",
-                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e},
+                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 4,
+                    "d2h_bytes_per_step": 4 + 16,  # the loss + the gradient range statistics of the step
+                    "ms_per_step": ms_e2e,
+                    "how": "module API (training_step, backward, all-reduce, Adam) fed by satflow_b200.prefetch."
+                           "DevicePrefetcher from PINNED HOST tensors: one cudaMemcpyAsync H2D of x and target per step "
+                           "on a side stream, double-buffered, so the copy of step i+1 overlaps step i (33 ms of PCIe "
+                           "under 165 ms of compute); the pipeline runs continuously through 2 warm-up and the K timed "
+                           "steps, so K copies fall inside the timed region; every step's loss is copied D2H and read "
+                           "on the host one step later"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
         line.update(extra)
