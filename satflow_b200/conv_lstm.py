@@ -7,7 +7,7 @@ The four cells and the Conv3d head are real torch modules used as parameter hold
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 import torch.nn as nn

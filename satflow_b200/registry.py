@@ -11,7 +11,7 @@ registered there as well, so ``satflow.models.create_model`` finds it.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Type
+from typing import Dict, List, Type
 
 _REGISTRY: Dict[str, Type] = {}
 

@@ -1,5 +1,5 @@
 """Quick device-side timing of the rollout (not the contract bench; see bench.py)."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
