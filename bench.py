@@ -65,7 +65,7 @@ def ncu_traffic(kernel_substr: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, read from the committed
     `ncu --set full` summary (tools/ncu_summary.py output under profiles/); (None, None) if no capture is committed."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for name in ("r2_ncu_full_summary.csv", "r1_v2_ncu_full_summary.csv"):
+    for name in ("r2b_ncu_full_summary.csv", "r2_ncu_full_summary.csv", "r1_v2_ncu_full_summary.csv"):
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.isfile(path):
             continue
@@ -558,14 +558,26 @@ def run_ours(args):
     if rank == 0:
         tr = parse_trace(_lib.trace_report())
         _lib.trace_enable(0)
+        # the fused dgrad launches that also carry the head's dgrad as a second K segment are the same kernel
+        hk, fk = "dgradT_fused2_kernel[+head dgrad]", "dgradT_fused2_kernel"
+        if hk in tr:
+            extra["fused_dgrad_with_head_segment"] = {"n_per_step": tr[hk][0] // 2, "avg_us": tr[hk][2],
+                                                      "plain_avg_us": tr.get(fk, (0, 0.0, None))[2]}
+            n0, ms0, _ = tr.get(fk, (0, 0.0, 0.0))
+            tr[fk] = (n0 + tr[hk][0], ms0 + tr[hk][1], (ms0 + tr[hk][1]) * 1e3 / (n0 + tr[hk][0]))
+            del tr[hk]
         fl = cell_step_flops(B, hid, hid, HW, HW)  # a cell step with a 64-channel input: K = (64 + 64) * 9
         npix = B * HW * HW
         gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
         # algorithmic bytes per launch (16-bit x / h / gates / dz, fp32 c / dc / dh; weights negligible)
         px = npix * hid
         by_cell = px * (2 + 2 + 4 + 2 + 4 + 8)            # x, h_prev, c_prev read; h, c, 4 gates written
-        by_fused = px * (8 + 4 + 8 + 4 + 4 + 4 + 8 + 8)    # dz read, dh_prev written; gates, c_prev, c_next, ONE dh source from HBM
-                                                           # (the other is this launch's dx, in shared memory), dc r/w, dz written
+        rc = args.dtype == "fp16" and os.environ.get("CLSTM_RECOMP_C", "1") != "0"
+        by_fused = px * (8 + 4 + 8 + 4 + (0 if rc else 4) + 4 + 8 + 8)  # dz read, dh_prev written; gates, c_prev, (c_next
+                                                           # unless it is recomputed from the gates), ONE dh source from HBM
+                                                           # (the other is this launch's dx, in shared memory; with the head
+                                                           # segment the head's G tile replaces dstack, same bytes), dc r/w,
+                                                           # dz written
         by_wgrad = px * (8 + 2 + 2)                        # dz, x, h_prev read
         by_dgrad = px * (8 + 4 + 4)                        # dz read, dx and dh_prev written
         tensor_kernels = {

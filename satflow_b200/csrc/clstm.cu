@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/clstm.h"
@@ -114,6 +115,10 @@ struct Knobs {
   int hybrid_wg = 2;        // CLSTM_HYBRID_WG: which wgrad worker variant the hybrid schedule uses (1 or 2)
   int wg_group = kWgMaxGroupBlocks;  // CLSTM_WG_GROUP: column blocks per wgrad CTA
   int overlap = 0;          // CLSTM_OVERLAP: wgrad on a side stream
+  int recomp_c = 1;         // CLSTM_RECOMP_C: the fused gate gradient rebuilds c' = f c + i g from the saved gates instead of
+                            // reading it (fp16 operands only: -8 % of the fused dgrad launch's HBM bytes)
+  int head_fuse = 1;        // CLSTM_HEAD_FUSE: the head's dgrad of frame t rides as a second K segment inside the fused dgrad
+                            // launch whose epilogue runs the top decoder cell's gate gradient of step t (no dstack)
   int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
   int graph = 1;            // CLSTM_GRAPH: launch-bound (small) rollouts replay their forward / backward as CUDA graphs
   void read() {
@@ -135,6 +140,8 @@ struct Knobs {
     wg_group = env_int("CLSTM_WG_GROUP", wg_group);
     if (wg_group < 1 || wg_group > kWgMaxGroupBlocks) wg_group = kWgMaxGroupBlocks;
     overlap = env_int("CLSTM_OVERLAP", overlap);
+    recomp_c = env_int("CLSTM_RECOMP_C", recomp_c);
+    head_fuse = env_int("CLSTM_HEAD_FUSE", head_fuse);
     persist = env_int("CLSTM_PERSIST", persist);
     graph = env_int("CLSTM_GRAPH", graph);
   }
@@ -623,11 +630,18 @@ int launch_dgradT(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT
   return after_launch("dgradT_kernel");
 }
 
+// The worker-warp generation of the fused kernel (dgradT_fused2.cuh) is selected and fits in shared memory.
+inline bool fused2_ok(const Ctx& cx) {
+  return (cx.knobs.fuse_workers == 2 || cx.knobs.fuse_workers == 4) &&
+         (cx.dev.smem_optin - static_cast<int>(dgradTf2_smem_bytes(0))) / kDtStageBytes >= 2;
+}
+
 // Transposed dgrad whose epilogue also runs the gate gradient of the NEXT cell step of the backward chain.
 template <typename E>
 int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
                         const CUtensorMap& x1, const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f,
-                        cudaStream_t st) {
+                        cudaStream_t st, const CUtensorMap* seg2_act = nullptr, const CUtensorMap* seg2_w = nullptr,
+                        int seg2_kblocks = 0) {
   const DeviceInfo& dev = cx.dev;
   DgradTParams p;
   memset(&p, 0, sizeof(p));
@@ -645,25 +659,34 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
   p.stages = stages;
   const int units = (p.num_m_tiles + 1) / 2;
   const int grid = units < dev.sms ? units : dev.sms;
-  if ((cx.knobs.fuse_workers == 2 || cx.knobs.fuse_workers == 4) && f.src2 == nullptr && f.fuse_units >= units) {
+  if (fused2_ok(cx) && f.src2 == nullptr && f.fuse_units >= units) {
     // second generation: drain warps + gate-gradient worker warps meeting at a staging ring (3 operand stages)
     int st2 = (dev.smem_optin - static_cast<int>(dgradTf2_smem_bytes(0))) / kDtStageBytes;
     if (st2 > kMaxStages) st2 = kMaxStages;
     if (st2 >= 2) {
       p.stages = st2;
+      p.extra = seg2_kblocks;
+      const CUtensorMap& gA = seg2_kblocks ? *seg2_act : dz128;
+      const CUtensorMap& gW = seg2_kblocks ? *seg2_w : wT;
       static bool attr2_set = false;
       if (!attr2_set) {
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
+        CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         attr2_set = true;
       }
+      // c' recomputed from the saved gates: 11-bit (fp16) gates only, see gate_grad_item4
+      const bool rc = cx.knobs.recomp_c && std::is_same<E, __half>::value;
       if (cx.knobs.fuse_workers == 4)
-        dgradT_fused2_kernel<E, 4><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, p, f);
+        dgradT_fused2_kernel<E, 4><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
+      else if (rc)
+        dgradT_fused2_kernel<E, 2, true><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
       else
-        dgradT_fused2_kernel<E, 2><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, p, f);
-      return after_launch("dgradT_fused2_kernel");
+        dgradT_fused2_kernel<E, 2><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
+      return after_launch(seg2_kblocks ? "dgradT_fused2_kernel[+head dgrad]" : "dgradT_fused2_kernel");
     }
   }
+  if (seg2_kblocks) return fail(CLSTM_EINVAL, "dgradT_fused: the second K segment needs the worker-warp kernel");
   static bool attr_set = false;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
@@ -795,13 +818,13 @@ int pack_cell(const Ctx& ctx, CellState& cs, const float* w, const float* bias, 
 template <typename E>
 int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int sn, const float* c_prev,
                       float* c_next, void* gates, cudaStream_t st, int cprev_slot = -1, int cnext_slot = -1,
-                      int gates_step = -1) {
+                      int gates_step = -1, bool zero_h = false) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   const CellGeom& g = cs.g;
   p.n_tiles = ctx.HP / 64;
   p.n_tile = 256;
-  p.nseg = 2;
+  p.nseg = zero_h ? 1 : 2;  // h == 0 (a cell's first step of a rollout): the h segment of the K loop is skipped
   if (g.in_col)
     p.seg[0] = ConvSeg{g.KIN / 64, 1, 1, in.b_off};
   else
@@ -877,7 +900,8 @@ inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
 // A source equal to cs.dxb is the dx this launch produces: it is consumed from shared memory and never written.
 template <typename E>
 int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const float* own, const float* e1,
-                     const float* e2, int buf, cudaStream_t st, int fuse_units = 0x7fffffff) {
+                     const float* e2, int buf, cudaStream_t st, int fuse_units = 0x7fffffff,
+                     const CUtensorMap* seg2_act = nullptr, const CUtensorMap* seg2_w = nullptr, int seg2_kblocks = 0) {
   const size_t npix = ctx.geo.npix();
   const int HP = ctx.HP;
   GateFuse f;
@@ -901,7 +925,8 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
   f.fuse_units = fuse_units;
   f.pf_dist = ctx.knobs.fuse_pf;
   return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT,
-                                ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0}, ctx.geo, ctx.geo.B, f, st);
+                                ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0}, ctx.geo, ctx.geo.B, f, st, seg2_act, seg2_w,
+                                seg2_kblocks);
 }
 
 // Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
@@ -943,11 +968,11 @@ int cell_wgrad(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, int fi
 template <typename E>
 int cell_backward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp, const void* gates,
                        const float* c_prev, const float* c_next, const float* dh0, const float* dh1,
-                       const float* dh2, cudaStream_t st) {
+                       const float* dh2, cudaStream_t st, bool need_dgrad = true) {
   const int first = cs.bwd_started ? 0 : 1;
   cs.bwd_started = true;
   RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, dh0, dh1, dh2, first, st));
-  RC_TRY(cell_dgrad<E>(ctx, cs, st));
+  if (need_dgrad) RC_TRY(cell_dgrad<E>(ctx, cs, st));
   RC_TRY(cell_wgrad<E>(ctx, cs, in, sp, first, st));
   return 0;
 }
@@ -1004,11 +1029,13 @@ struct clstm_plan {
   void* wz = nullptr;         // E [HP/64][144][64]: taps as output columns (head_rows.cuh); null if c_out > 16
   float* bias_h = nullptr;    // fp32 [NT]
   void* whd = nullptr;        // E [n_tile_hd rows = HP][KG]
+  void* whdT = nullptr;       // E [128][KG]: rows [0, HP) = whd, the rest zero — the A operand of the head's dgrad when it
+                              // rides inside the fused dgrad of decoder cell 0 (rows = that cell's x | h channel split)
   float* hpart = nullptr;     // fp32 [splits][128*(KG/128)][HP]
   float* hbpart = nullptr;    // fp32 [C_out][batch * hb_chunks]
   int hb_chunks = 1;          // pieces per (b, c) run in head_grad_stats_kernel
   int head_splits = 0, head_group = 0, n_tile_hd = 0;
-  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_dstack16, m_wz;
+  CUtensorMap m_xcol128, m_xcol64, m_G128, m_G64, m_wh, m_whd, m_whdT, m_dstack16, m_wz;
   // persistent forward chain (rollout_persist.cuh): device copies of the tensor maps and of the step table
   bool persist_ok = false;
   int persist_stages = 0;
@@ -1047,6 +1074,7 @@ void carve_plan(clstm_plan* p, uint8_t* base) {
     p->G = cv.take<void>(npix * p->KG * 2);
     p->dstack = cv.take<float>(npix * HP * 4);
     p->whd = cv.take<void>(static_cast<size_t>(HP) * p->KG * 2);
+    p->whdT = cv.take<void>(static_cast<size_t>(128) * p->KG * 2);
     p->hpart = cv.take<float>(static_cast<size_t>(p->head_splits) * p->KG * HP * 4);
     {  // about 8 blocks per SM, at least 4096 elements per block
       const size_t per_b = static_cast<size_t>(c.t_out) * c.height * c.width;
@@ -1112,6 +1140,7 @@ int persist_setup(clstm_plan* p, cudaStream_t st) {
     pc.seg[0] = g.in_col ? ConvSeg{g.KIN / 64, 1, 1, 0} : ConvSeg{g.CIP / 64, g.kh, g.kw, 0};
     pc.seg[1] = ConvSeg{ctx.HP / 64, g.kh, g.kw, 0};
     pc.kblocks = cs.Kf / 64;
+    pc.kb_first = pc.seg[0].chunks * pc.seg[0].kh * pc.seg[0].kw;
     pc.map_a1 = base + 0, pc.map_b = base + 1, pc.map_xc = base + 2, pc.map_xh = base + 3, pc.map_xg = base + 4;
     pc.bias = cs.bias_p;
   }
@@ -1195,6 +1224,12 @@ int plan_set_weights(clstm_plan* p, const float* const* params, cudaStream_t st)
     pack_head_weights_dgrad_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, static_cast<E*>(p->whd), p->cfg.out_channels,
                                                                    p->cfg.hidden, p->ctx.HP, p->KG);
     RC_TRY(after_launch("pack_head_weights_dgrad_kernel"));
+    if (p->ctx.HP <= 128) {
+      CU_TRY(cudaMemsetAsync(p->whdT, 0, static_cast<size_t>(128) * p->KG * 2, st));
+      pack_head_weights_dgrad_kernel<E><<<kPackBlocks, 256, 0, st>>>(wh, static_cast<E*>(p->whdT), p->cfg.out_channels,
+                                                                     p->cfg.hidden, p->ctx.HP, p->KG);
+      RC_TRY(after_launch("pack_head_weights_dgrad_kernel"));
+    }
   }
   return 0;
 }
@@ -1236,7 +1271,7 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
     void* gates = c.training ? static_cast<void*>(static_cast<E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP)
                              : nullptr;
     return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st, cslot(cs, t),
-                                cslot(cs, t + 1), t);
+                                cslot(cs, t + 1), t, /*zero_h=*/t == 0);
   };
   if (p->persist_ok) {
     RC_TRY(launch_persist<E>(p, st));  // the whole chain below in one launch, c resident in TMEM
@@ -1338,7 +1373,9 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
     const float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
     const float* own = (t == cs.T - 1) ? nullptr : cs.dh_own;
-    if (!overlap) return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st);
+    if (!overlap)
+      return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st,
+                                   /*need_dgrad=*/cs.with_x || t > 0);
     const int buf = nstep & 1;
     const int first = cs.bwd_started ? 0 : 1;
     cs.bwd_started = true;
@@ -1355,7 +1392,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
 
   CellState& last = p->cells[ncell - 1];
   // head backward for output frame t: dlogit "col" tensor -> dgrad into dstack, wgrad accumulation
-  auto head_back = [&](int t) -> int {
+  auto head_back = [&](int t, bool with_dgrad = true) -> int {
     bool tiled = false;
     RC_TRY((launch_row_im2col<E, 1>(dy, y, static_cast<E*>(p->G), c.batch, c.t_out, c.out_channels, c.height, c.width,
                                     3, 3, p->KG, t, 1, ctx.scale, st, &tiled)));
@@ -1364,7 +1401,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
                                                            c.t_out, c.height, c.width, p->KG, t, 1, ctx.scale);
       RC_TRY(after_launch("head_grad_col_kernel"));
     }
-    {
+    if (with_dgrad) {
       ConvGemmParams hp;
       memset(&hp, 0, sizeof(hp));
       hp.n_tile = p->n_tile_hd;
@@ -1440,7 +1477,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
         RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b));
       }
       gate_done = false;
-      RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      if (cs.with_x || o.t > 0) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
       if (n + 1 < ops.size()) {
         const BackOp& nx = ops[n + 1];
         CellState& cn = p->cells[nx.k];
@@ -1501,7 +1538,12 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
         const BackOp& nx = ops[n + 1];
         CellState& cn = p->cells[nx.k];
         if (nx.k != o.k) {
-          if (nx.head) RC_TRY(head_back(nx.t));  // dstack must be ready; nothing in flight still reads it
+          // The head's dgrad of frame nx.t is one more contribution to the consumer's dh: instead of a launch of its
+          // own writing dstack (fp32, re-read by the gate gradient), its K = KG columns are appended to this dgrad's
+          // K loop (rows of the x part, i.e. the channels of the top decoder cell's h) — dstack does not exist.
+          const bool head_in_gemm = nx.head && ctx.knobs.head_fuse && cs.with_x && cs.g.CIP == 64 && hybrid_units == 0 &&
+                                    fused2_ok(ctx) && nx.e1 == p->dstack && nx.e2 == cs.dxb;
+          if (nx.head) RC_TRY(head_back(nx.t, !head_in_gemm));  // dstack / G must be ready; nothing in flight reads them
           const float* own_n = (nx.t == cn.T - 1) ? nullptr : cn.dh_own;
           int fuse_units = 0x7fffffff;
           if (hybrid_units > 0 && cs.with_x) {
@@ -1522,12 +1564,17 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
             gw.pix_begin = static_cast<unsigned>(hybrid_units) * 256u;
             gwp = &gw;
           }
-          RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nx.e1, nx.e2, b, st, fuse_units));
+          if (head_in_gemm)
+            RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nullptr, nx.e2, b, st, fuse_units, &p->m_G128,
+                                       &p->m_whdT, p->KG / 64));
+          else
+            RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nx.e1, nx.e2, b, st, fuse_units));
           fused_here = true;
           gate_done = true;
         }
       }
-      if (!fused_here) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      // the bottom cell's step 0 has nobody to hand a gradient to: its dgrad would only produce d(initial h) = unused
+      if (!fused_here && (cs.with_x || o.t > 0)) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
       RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b, gwp));
       if (fused_here) b ^= 1;
     }
@@ -1980,6 +2027,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     RC_TRY(make_map_act(&p->m_G128, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW, g.BH));
     RC_TRY(make_map_act(&p->m_G64, ctx.dtype, p->G, p->KG, g.W, g.H, c.batch, g.BW2, g.BH2));
     RC_TRY(make_map_w(&p->m_whd, ctx.dtype, p->whd, p->KG, ctx.HP, p->n_tile_hd));
+    RC_TRY(make_map_w(&p->m_whdT, ctx.dtype, p->whdT, p->KG, 128, 128));
     RC_TRY(make_map_epi(&p->m_dstack16, 4, ctx.dtype, p->dstack, ctx.HP, g.W, g.H, c.batch, g.BW, g.BH));
   }
   RC_TRY(persist_setup(p, st));

@@ -32,6 +32,8 @@ struct DgradTParams {
   int split_col;   // output channels [0, split) -> X0 (dx), [split, ...) -> X1 (dh_prev); multiple of 64
   int lbw;         // log2(BW)
   int rotate;      // 1: unit u starts its K loop at k-block u % kblocks (spreads the concurrent weight reads over L2)
+  int extra;       // dgradT_fused2_kernel only: k-blocks of a SECOND, un-shifted K segment (tmG / tmW2) appended to the
+                   // K loop — the head's dgrad for the consumer's output frame, accumulated into the same TMEM tile
 };
 
 inline size_t dgradT_smem_bytes(int stages) {

@@ -30,10 +30,12 @@ inline size_t dgradTf2_smem_bytes(int stages) {
          (2 * kMaxStages + 4 + 8) * 8 + 16 + 64;
 }
 
-template <typename E, int WSETS>
+// RC: c' of the consumer step is recomputed from its saved gates and c_prev instead of being read (gate_grad_item4).
+template <typename E, int WSETS, bool RC = false>
 __global__ void __launch_bounds__(kDf2Threads, 1)
 dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW,
-                     const __grid_constant__ CUtensorMap tmX1, const DgradTParams p, const GateFuse f) {
+                     const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmG,
+                     const __grid_constant__ CUtensorMap tmW2, const DgradTParams p, const GateFuse f) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_stg = smem + p.stages * kDtStageBytes;           // [team][buffer][kDf2StgBuf]
@@ -54,6 +56,10 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmDz);
     tma_prefetch_desc(&tmW);
+    if (p.extra) {
+      tma_prefetch_desc(&tmG);
+      tma_prefetch_desc(&tmW2);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -117,12 +123,28 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
               phase ^= 1;
             }
           }
+          // second K segment (p.extra k-blocks, no taps): the head's dlogit "col" tensor of the consumer's output
+          // frame against the head dgrad weights, so dx already contains the head's share of the consumer's dh
+          for (int j = 0; j < p.extra; ++j) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* dst = smem + stage * kDtStageBytes;
+            if (lane == 0) {
+              mbar_expect_tx(&full_bar[stage], kDtStageBytes);
+              tma_load_2d(dst, &tmW2, &full_bar[stage], j * kBlockK, 0);
+            } else {
+              tma_load_4d(dst + 16384 + (lane - 1) * kABytes, &tmG, &full_bar[stage], j * kBlockK, w0, h0, b);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = make_idesc(Elem<E>::kFmt, 128, 256, 0, 0);
-        const int kblocks = taps * p.seg.chunks;
+        const int kblocks = taps * p.seg.chunks + p.extra;
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         uint64_t adesc = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
@@ -264,7 +286,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       r.g[2] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 128));
       r.g[3] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 192));
       r.cp = cp_c ? __ldg(reinterpret_cast<const float4*>(cp_c + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      r.cn = __ldg(reinterpret_cast<const float4*>(cn_c + o1));
+      if constexpr (!RC) r.cn = __ldg(reinterpret_cast<const float4*>(cn_c + o1));
       r.dc = *reinterpret_cast<const float4*>(dc_c + o1);  // read and written by this thread only
       if (s0_c) r.s0 = __ldg(reinterpret_cast<const float4*>(s0_c + o1));
       if (s1_c) r.s1 = __ldg(reinterpret_cast<const float4*>(s1_c + o1));
@@ -280,7 +302,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       if (s1_c) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
       float4 dcn;
       uint2 dzp[4];
-      gate_grad_item4<E>(r.g, r.cp, r.cn, r.dc, dhv, bsum, zmax, dcn, dzp);
+      gate_grad_item4<E, RC>(r.g, r.cp, r.cn, r.dc, dhv, bsum, zmax, dcn, dzp);
       const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;
       *reinterpret_cast<float4*>(dc_c + o1) = dcn;
 #pragma unroll

@@ -478,7 +478,10 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
 // that ride inside the GEMM kernels (dgradT_fused_kernel's epilogue, the worker warps of wgrad_kernel).
 //   g[a]: the four saved gates (packed 16-bit x4), cp / cn: c_prev / c_next, dcin: incoming dc, dhv: summed dh sources
 //   -> dz_out[a] packed 16-bit, dc_out = dct * f, bsum += dz (bias-gradient partial), zmax = running packed max |dz|
-template <typename E>
+// RC (recompute c'): cn4 is ignored and c' = f * c_prev + i * g is rebuilt from the saved (16-bit) gates — the same
+// rounded gates every other term of the gradient already uses — which removes one fp32 stream (8 % of the fused
+// launch's HBM bytes).  Only with 11-bit gates (fp16); bf16 gates would put 2^-9 of c' into tanh(c').
+template <typename E, bool RC = false>
 __device__ __forceinline__ void gate_grad_item4(const uint2 (&g)[4], const float4& cp4, const float4& cn4,
                                                 const float4& dcin, const float (&dhv)[4], float (&bsum)[4][4],
                                                 uint32_t& zmax, float4& dc_out, uint2 (&dz_out)[4]) {
@@ -495,7 +498,7 @@ __device__ __forceinline__ void gate_grad_item4(const uint2 (&g)[4], const float
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float gi = gv[0][e], gf = gv[1][e], go = gv[2][e], gg = gv[3][e];
-    const float tc = fast_tanh(cn[e]);
+    const float tc = fast_tanh(RC ? fmaf(gf, cp[e], gi * gg) : cn[e]);
     const float d_o = dhv[e] * tc;
     const float dct = fmaf(dhv[e] * go, 1.f - tc * tc, dcv[e]);
     dzv[0][e] = dct * gg * gi * (1.f - gi);

@@ -29,6 +29,8 @@ constexpr int kPersistMaxMaps = 32;
 struct PersistCell {
   ConvSeg seg[2];   // [0] the cell's input (x im2col or the h of another cell), [1] its own h; b_off unused here
   int kblocks;
+  int kb_first;     // k-blocks of seg[0] alone: a cell's first step sees h == 0, so its h segment is skipped (the same
+                    // K range and rotation as the per-step launch with nseg = 1 -> bit-identical results)
   int map_a1, map_b, map_xc, map_xh, map_xg;  // indices into the tensor-map table (map_xc / map_xg: training only)
   const float* bias;                          // packed [n_tiles * 256]
 };
@@ -139,8 +141,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) rollout_persist_kernel(const 
           }
           fence_proxy_async_all();
         }
-        int kb = p.rotate ? (mt % (p.tiles_w * p.tiles_h) + nt) % c.kblocks : 0;
-        for (int i = 0; i < c.kblocks; ++i) {
+        const int nkb = st.first ? c.kb_first : c.kblocks;
+        int kb = (p.rotate && nkb > 1) ? (mt % (p.tiles_w * p.tiles_h) + nt) % nkb : 0;
+        for (int i = 0; i < nkb; ++i) {
           const int4 e = kt[kb];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * stage_bytes;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) rollout_persist_kernel(const 
           } else {
             tma_load_2d(a_dst + kABytes, mapB, &full_bar[stage], kb * kBlockK, nt * 256);
           }
-          if (++kb == c.kblocks) kb = 0;
+          if (++kb == nkb) kb = 0;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) rollout_persist_kernel(const 
       uint64_t adesc = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + kABytes, 16, 1024);
       for (int s = 0; s < p.nsteps; ++s) {
-        const int kblocks = p.cells[p.steps[s].cell].kblocks;
+        const int kblocks = p.steps[s].first ? p.cells[p.steps[s].cell].kb_first : p.cells[p.steps[s].cell].kblocks;
         mbar_wait(&tmem_empty[0], (static_cast<uint32_t>(s) & 1) ^ 1);
         tcgen05_fence_after();
         for (int kb = 0; kb < kblocks; ++kb) {
