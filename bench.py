@@ -583,6 +583,8 @@ def run_ours(args):
         tensor_kernels = {
             "cell_step": ("convgemm_kernel<EPI_LSTM>: fused conv + LSTM cell step (training variant, also writes gates)",
                           "convgemm_kernel<__half, 0>", by_cell),
+            "cell_step[pair]": ("cellstep_pair_kernel: fused conv + LSTM cell step on CTA pairs (cta_group::2; training "
+                                "variant, also writes gates)", "cellstep_pair_kernel", by_cell),
             "dgradT_fused2_kernel": ("dgradT_fused2_kernel: data gradient + gate gradient of the next chain step on "
                                      "dedicated worker warps", "dgradT_fused", by_fused),
             "dgradT_fused_kernel": ("dgradT_fused_kernel: data gradient + fused gate gradient of the next chain step",

@@ -23,6 +23,7 @@
 #include "dgradT.cuh"
 #include "dgradT_fused2.cuh"
 #include "head_rows.cuh"
+#include "cellstep_pair.cuh"
 #include "pointwise.cuh"
 #include "rollout_persist.cuh"
 #include "wgrad.cuh"
@@ -119,6 +120,8 @@ struct Knobs {
                             // reading it (fp16 operands only: -8 % of the fused dgrad launch's HBM bytes)
   int head_fuse = 1;        // CLSTM_HEAD_FUSE: the head's dgrad of frame t rides as a second K segment inside the fused dgrad
                             // launch whose epilogue runs the top decoder cell's gate gradient of step t (no dstack)
+  int pair = 1;             // CLSTM_PAIR: cell step on CTA pairs (cta_group::2, cellstep_pair.cuh) for shapes with at least two
+                            // waves of tiles
   int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
   int graph = 1;            // CLSTM_GRAPH: launch-bound (small) rollouts replay their forward / backward as CUDA graphs
   void read() {
@@ -142,6 +145,7 @@ struct Knobs {
     overlap = env_int("CLSTM_OVERLAP", overlap);
     recomp_c = env_int("CLSTM_RECOMP_C", recomp_c);
     head_fuse = env_int("CLSTM_HEAD_FUSE", head_fuse);
+    pair = env_int("CLSTM_PAIR", pair);
     persist = env_int("CLSTM_PERSIST", persist);
     graph = env_int("CLSTM_GRAPH", graph);
   }
@@ -439,7 +443,7 @@ struct CellState {
   float* dc = nullptr;      // fp32 [npix][HP]
   float* wpart = nullptr;   // fp32 [splits][4HP][Kf]
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
-  CUtensorMap m_h128, m_h64, m_wp, m_wd;
+  CUtensorMap m_h128, m_h64, m_wp, m_wp128, m_wd;  // m_wp128: 128-row weight boxes (a CTA pair's halves)
   CUtensorMap m_h66;                                // wgrad halo rows: box 64 ch x 66 px x 1 row
   CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
@@ -530,6 +534,7 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_act(&cs.m_h64, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW2, g.BH2));
   if (g.BW2 == 64 && g.BH2 == 1) RC_TRY(make_map_act(&cs.m_h66, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, 66, 1));
   RC_TRY(make_map_w(&cs.m_wp, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 256));
+  RC_TRY(make_map_w(&cs.m_wp128, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
   if (ctx.training)
     RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
   RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
@@ -592,6 +597,42 @@ int launch_convgemm(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1,
   const int grid = total < dev.sms ? total : dev.sms;
   convgemm_kernel<E, EPI><<<grid, kGemmThreads, smem, st>>>(a0, a1, b, x0 ? *x0 : b, x1 ? *x1 : b, x2 ? *x2 : b,
                                                             x3 ? *x3 : (x0 ? *x0 : b), p);
+  return after_launch(name);
+}
+
+// Cell step on CTA pairs (cellstep_pair.cuh): shapes with at least two waves of tiles and an even number of tiles per
+// image; `used` stays false otherwise (the caller then launches convgemm_kernel<E, EPI_LSTM>).
+template <typename E>
+int launch_cellstep_pair(const Ctx& cx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b128,
+                         ConvGemmParams p, const Geo& g, cudaStream_t st, const CUtensorMap& xc, const CUtensorMap& xh,
+                         const CUtensorMap& xg, const char* name, bool* used) {
+  *used = false;
+  const DeviceInfo& dev = cx.dev;
+  if (!cx.knobs.pair || cx.knobs.staged != 1 || p.n_tile != 256) return 0;
+  const int tiles_img = g.tiles_w * g.tiles_h;
+  const long long m_tiles = static_cast<long long>(g.B) * tiles_img;
+  int kblocks = 0;
+  for (int s = 0; s < p.nseg; ++s) kblocks += p.seg[s].chunks * p.seg[s].kh * p.seg[s].kw;
+  if ((tiles_img & 1) || m_tiles * p.n_tiles < 2ll * dev.sms || kblocks > kKtabMax || kblocks < 1) return 0;
+  p.B = g.B, p.H = g.H, p.W = g.W;
+  p.BW = g.BW, p.BH = g.BH, p.tiles_w = g.tiles_w, p.tiles_h = g.tiles_h;
+  p.num_m_tiles = static_cast<int>(m_tiles);
+  p.staged = 1;
+  p.rotate = (kblocks > 1 && cx.knobs.rotate) ? 1 : 0;
+  int stages = (dev.smem_optin - static_cast<int>(cellstep_pair_smem_bytes(0, p.n_tiles))) / kPairStageBytes;
+  if (stages > cx.knobs.stages) stages = cx.knobs.stages;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return 0;
+  p.stages = stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(cellstep_pair_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
+    attr_set = true;
+  }
+  const int grid = dev.sms & ~1;
+  cellstep_pair_kernel<E><<<grid, kGemmThreads, cellstep_pair_smem_bytes(stages, p.n_tiles), st>>>(a0, a1, b128, xc, xh, xg,
+                                                                                                 xc, p);
+  *used = true;
   return after_launch(name);
 }
 
@@ -841,6 +882,13 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
     p.cnext_boff = cnext_slot * ctx.geo.B;
     p.hnext_boff = sn * ctx.geo.B;
     p.gates_boff = (gates != nullptr && gates_step >= 0) ? gates_step * ctx.geo.B : -1;
+    if (!g.in_col || ctx.knobs.pair >= 2) {  // the short-K bottom cell is epilogue bound: measured 2 % slower on pairs
+      bool used = false;
+      RC_TRY((launch_cellstep_pair<E>(ctx, *in.map128, cs.m_h128, cs.m_wp128, p, ctx.geo, st, cs.m_c16, cs.m_h16,
+                                      ctx.training ? cs.m_g16 : cs.m_h16, g.in_col ? "cell_step[x im2col, pair]" : "cell_step[pair]",
+                                      &used)));
+      if (used) return 0;
+    }
     return launch_convgemm<E, EPI_LSTM>(ctx, *in.map128, cs.m_h128, cs.m_wp, p, ctx.geo, ctx.geo.B, st, &cs.m_c16,
                                         &cs.m_h16, ctx.training ? &cs.m_g16 : &cs.m_h16, nullptr,
                                         g.in_col ? "cell_step[x im2col]" : "cell_step", &cs.m_c8, &cs.m_h8,
