@@ -14,7 +14,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --c
 python tools/launch_summary.py gpurun_out/${R}_launches_train_step.csv > gpurun_out/${R}_launches_train_step_summary.txt 2>/dev/null
 head -12 gpurun_out/${R}_launches_train_step_summary.txt
 i=0
-for spec in "convgemm_kernel:30:1" "dgradT_fused:30:1" "wgrad_kernel:30:2" "head_rows_kernel:0:1" "gate_grad_kernel:0:1"; do
+for spec in "convgemm_kernel:3:1" "cellstep_pair_kernel:30:1" "dgradT_fused:30:2" "wgrad_kernel:30:2" "head_rows_kernel:0:1" "gate_grad_kernel:0:1"; do
   i=$((i+1))
   k=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; cnt=${rest#*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c $cnt \
@@ -25,4 +25,8 @@ done
 PROF_SMALL=1 timeout 300 ncu --set full --clock-control none --import-source on -k "regex:rollout_persist" -s 1 -c 1 \
   -o gpurun_out/${R}_full_persist -f python tools/prof_target.py > gpurun_out/ncu_full_p.log 2>&1
 tail -1 gpurun_out/ncu_full_p.log
-ls -la gpurun_out/*.ncu-rep
+# gpurun merges at most 64 MiB back: summarise on the box, keep only the fused-dgrad report (source view)
+python tools/ncu_summary.py gpurun_out/${R}_full_*.ncu-rep > gpurun_out/${R}_ncu_full_summary.csv 2>/dev/null
+cat gpurun_out/${R}_ncu_full_summary.csv | cut -c1-400
+for f in gpurun_out/${R}_full_*.ncu-rep; do case "$f" in *_full_3.ncu-rep) ;; *) rm -f "$f";; esac; done
+ls -la gpurun_out/
