@@ -142,6 +142,7 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     }
     fence_barrier_init();
   }
+  // a cta_group::2 allocation is performed by one warp of EACH CTA of the pair (blackwell guide, 'tensor_allocator')
   if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
   for (int i = threadIdx.x; i < p.n_tiles * 256; i += blockDim.x) bias_s[i] = p.bias[i];
   if (threadIdx.x < kblocks) {

@@ -21,6 +21,10 @@ for env in ({"CLSTM_PERSIST": "0", "CLSTM_GRAPH": "0"}, {"CLSTM_FUSE_WORKERS": "
     print(env, max(r.values()))
     for k in env:
         del os.environ[k]
+# session 2: the CTA-pair cell step (cta_group::2; needs two waves of tiles: 384 here) and, in every rollout above, the
+# fused dgrad with the head's dgrad as a second K segment and c' recomputed from the gates
+r = G.rollout_case(1, 1, 2, 12, 64, 12, 128, 384, states=False)
+print("pair", max(r.values()))
 r = G.cell_unrolled_case(1, 12, 16, 6, 20, 3)
 print("unrolled cell", max(r.values()))
 cell = ConvLSTMCell(12, 32, (3, 3), True).cuda()
