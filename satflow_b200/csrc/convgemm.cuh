@@ -281,7 +281,10 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const int w0 = (mt % p.tiles_w) * p.BW;
           const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
           const int b = mt / (p.tiles_w * p.tiles_h);
-          int kb = (mt % (p.tiles_w * p.tiles_h) + nt) % kblocks;  // position inside the image: batch-index independent
+          // position inside the image: batch-index independent.  Keyed on the EVEN tile of a pair so that the CTA-pair
+          // kernel (cellstep_pair.cuh: one K order per pair) and this one accumulate every tile in the same order —
+          // which kernel runs depends on the batch size, a sample's bits must not.
+          int kb = (((mt % (p.tiles_w * p.tiles_h)) & ~1) + nt) % kblocks;
           for (int i = 0; i < kblocks; ++i) {
             const int4 e = ktab[kb];
             mbar_wait(&empty_bar[stage], phase ^ 1);

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) rollout_persist_kernel(const 
           fence_proxy_async_all();
         }
         const int nkb = st.first ? c.kb_first : c.kblocks;
-        int kb = (p.rotate && nkb > 1) ? (mt % (p.tiles_w * p.tiles_h) + nt) % nkb : 0;
+        int kb = (p.rotate && nkb > 1) ? (((mt % (p.tiles_w * p.tiles_h)) & ~1) + nt) % nkb : 0;  // as convgemm.cuh
         for (int i = 0; i < nkb; ++i) {
           const int4 e = kt[kb];
           mbar_wait(&empty_bar[stage], phase ^ 1);
