@@ -573,7 +573,8 @@ def run_ours(args):
         px = npix * hid
         by_cell = px * (2 + 2 + 4 + 2 + 4 + 8)            # x, h_prev, c_prev read; h, c, 4 gates written
         rc = args.dtype == "fp16" and os.environ.get("CLSTM_RECOMP_C", "1") != "0"
-        by_fused = px * (8 + 4 + 8 + 4 + (0 if rc else 4) + 4 + 8 + 8)  # dz read, dh_prev written; gates, c_prev, (c_next
+        s16 = rc and os.environ.get("CLSTM_STATE16", "1") != "0"   # dh_prev / own dh / dc in 16 bits
+        by_fused = px * (8 + (2 if s16 else 4) + 8 + 4 + (0 if rc else 4) + (2 if s16 else 4) + (4 if s16 else 8) + 8)  # dz read, dh_prev written; gates, c_prev, (c_next
                                                            # unless it is recomputed from the gates), ONE dh source from HBM
                                                            # (the other is this launch's dx, in shared memory; with the head
                                                            # segment the head's G tile replaces dstack, same bytes), dc r/w,

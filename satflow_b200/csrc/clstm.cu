@@ -120,6 +120,8 @@ struct Knobs {
                             // reading it (fp16 operands only: -8 % of the fused dgrad launch's HBM bytes)
   int head_fuse = 1;        // CLSTM_HEAD_FUSE: the head's dgrad of frame t rides as a second K segment inside the fused dgrad
                             // launch whose epilogue runs the top decoder cell's gate gradient of step t (no dstack)
+  int state16 = 1;          // CLSTM_STATE16: dc and the cells' own dh_prev in 16 bits (at the dz scale) between the launches of the fused
+                            // backward chain (fp16 operands, worker-warp fused dgrad with recomputed c' only)
   int pair = 1;             // CLSTM_PAIR: cell step on CTA pairs (cta_group::2, cellstep_pair.cuh) for shapes with at least two
                             // waves of tiles
   int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
@@ -145,6 +147,7 @@ struct Knobs {
     overlap = env_int("CLSTM_OVERLAP", overlap);
     recomp_c = env_int("CLSTM_RECOMP_C", recomp_c);
     head_fuse = env_int("CLSTM_HEAD_FUSE", head_fuse);
+    state16 = env_int("CLSTM_STATE16", state16);
     pair = env_int("CLSTM_PAIR", pair);
     persist = env_int("CLSTM_PERSIST", persist);
     graph = env_int("CLSTM_GRAPH", graph);
@@ -335,14 +338,18 @@ int make_map_epi(CUtensorMap* m, int elem_bytes, int dtype16, const void* ptr, i
 
 // fp32 [N][H][W][C] tensor written in [16 px along W] x 64-channel boxes (256-byte rows, no swizzle): the
 // transposed dgrad's output blocks.
-int make_map_out64(CUtensorMap* m, const void* ptr, int C, int W, int H, long long N) {
+int make_map_out64(CUtensorMap* m, const void* ptr, int C, int W, int H, long long N, int dtype16 = -1) {
+  // dtype16 < 0: fp32 elements; CLSTM_F16 / CLSTM_BF16: 16-bit elements (the 16-bit dh_prev of the default backward schedule)
   EncodeTiledFn enc;
   RC_TRY(get_encode(&enc));
+  const cuuint64_t eb = dtype16 < 0 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
   cuuint32_t box[4] = {64, 16, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+  const CUtensorMapDataType dt = dtype16 < 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (dtype16 == CLSTM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(m, dt, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CLSTM_ECUDA, "cuTensorMapEncodeTiled(out64 C=%d W=%d H=%d) -> %d", C, W, H, (int)r);
@@ -445,7 +452,8 @@ struct CellState {
   float* bpart = nullptr;   // fp32 [kGateGradBlocks][4HP]
   CUtensorMap m_h128, m_h64, m_wp, m_wp128, m_wd;  // m_wp128: 128-row weight boxes (a CTA pair's halves)
   CUtensorMap m_h66;                                // wgrad halo rows: box 64 ch x 66 px x 1 row
-  CUtensorMap m_wdT, m_dxT, m_dhT;                  // transposed dgrad: 128-row weight boxes, 64-channel output boxes
+  CUtensorMap m_wdT, m_dxT, m_dhT, m_dhT16;         // transposed dgrad: 128-row weight boxes, 64-channel output boxes
+                                                    // (m_dhT16: dh_own viewed as 16-bit elements, CLSTM_STATE16)
   CUtensorMap m_c16, m_h16, m_g16, m_dh16, m_dx16;  // epilogue (staged store / c_prev load) maps
   CUtensorMap m_c8, m_h8, m_g8;                     // the same with 8-channel boxes (CLSTM_STAGED=2)
 
@@ -552,6 +560,7 @@ int map_cell(CellState& cs, const Ctx& ctx) {
     RC_TRY(make_map_epi(&cs.m_dh16, 4, ctx.dtype, cs.dh_own, ctx.HP, g.W, g.H, g.B, g.BW, g.BH));
     RC_TRY(make_map_w(&cs.m_wdT, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, 128));
     RC_TRY(make_map_out64(&cs.m_dhT, cs.dh_own, ctx.HP, g.W, g.H, g.B));
+    RC_TRY(make_map_out64(&cs.m_dhT16, cs.dh_own, ctx.HP, g.W, g.H, g.B, ctx.dtype));
     if (cs.with_x) RC_TRY(make_map_out64(&cs.m_dxT, cs.dxb, cs.g.CIP, g.W, g.H, g.B));
     if (cs.with_x) RC_TRY(make_map_epi(&cs.m_dx16, 4, ctx.dtype, cs.dxb, cs.g.CIP, g.W, g.H, g.B, g.BW, g.BH));
   }
@@ -682,7 +691,7 @@ template <typename E>
 int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT, const CUtensorMap& x0,
                         const CUtensorMap& x1, const ConvSeg& seg, const Geo& g, long long images, const GateFuse& f,
                         cudaStream_t st, const CUtensorMap* seg2_act = nullptr, const CUtensorMap* seg2_w = nullptr,
-                        int seg2_kblocks = 0) {
+                        int seg2_kblocks = 0, bool state16 = false) {
   const DeviceInfo& dev = cx.dev;
   DgradTParams p;
   memset(&p, 0, sizeof(p));
@@ -714,11 +723,16 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
+        CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         attr2_set = true;
       }
       // c' recomputed from the saved gates: 11-bit (fp16) gates only, see gate_grad_item4
       const bool rc = cx.knobs.recomp_c && std::is_same<E, __half>::value;
-      if (cx.knobs.fuse_workers == 4)
+      if (state16) {
+        if (!rc || cx.knobs.fuse_workers != 2)
+          return fail(CLSTM_EINVAL, "dgradT_fused: 16-bit states need CLSTM_FUSE_WORKERS=2 and CLSTM_RECOMP_C=1");
+        dgradT_fused2_kernel<E, 2, true, true><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
+      } else if (cx.knobs.fuse_workers == 4)
         dgradT_fused2_kernel<E, 4><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
       else if (rc)
         dgradT_fused2_kernel<E, 2, true><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
@@ -727,7 +741,8 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
       return after_launch(seg2_kblocks ? "dgradT_fused2_kernel[+head dgrad]" : "dgradT_fused2_kernel");
     }
   }
-  if (seg2_kblocks) return fail(CLSTM_EINVAL, "dgradT_fused: the second K segment needs the worker-warp kernel");
+  if (seg2_kblocks || state16)
+    return fail(CLSTM_EINVAL, "dgradT_fused: the second K segment / 16-bit states need the worker-warp kernel");
   static bool attr_set = false;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(dgradT_fused_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin));
@@ -902,13 +917,14 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
 // accumulation.  dh sources (fp32 NHWC, scaled by S) may be null.  c_prev may be null (zeros).
 template <typename E>
 int cell_gate_grad(const Ctx& ctx, CellState& cs, const void* gates, const float* c_prev, const float* c_next,
-                   const float* dh0, const float* dh1, const float* dh2, int first, cudaStream_t st, int buf = 0) {
+                   const float* dh0, const float* dh1, const float* dh2, int first, cudaStream_t st, int buf = 0,
+                   bool state16 = false) {
   // pointwise gate gradient (backward of layers/ConvLSTM.py:48-55).  (Forcing the max-shared-memory carveout so
   // it could co-reside with a wgrad CTA slows it from 442 to 614 us — it needs L1 for its loads in flight — and the
   // two kernels still did not overlap: DESIGN.md "backward overlap".)
   gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 9 * sizeof(float), st>>>(
       static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dzb[buf]), cs.bpart,
-      !first, ctx.geo.npix(), ctx.HP, ctx.amax + 1);
+      !first, ctx.geo.npix(), ctx.HP, ctx.amax + 1, state16 ? 1 : 0);
   return after_launch("gate_grad_kernel");
 }
 
@@ -949,7 +965,8 @@ inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
 template <typename E>
 int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const float* own, const float* e1,
                      const float* e2, int buf, cudaStream_t st, int fuse_units = 0x7fffffff,
-                     const CUtensorMap* seg2_act = nullptr, const CUtensorMap* seg2_w = nullptr, int seg2_kblocks = 0) {
+                     const CUtensorMap* seg2_act = nullptr, const CUtensorMap* seg2_w = nullptr, int seg2_kblocks = 0,
+                     bool state16 = false) {
   const size_t npix = ctx.geo.npix();
   const int HP = ctx.HP;
   GateFuse f;
@@ -972,9 +989,9 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
   f.HP = HP;
   f.fuse_units = fuse_units;
   f.pf_dist = ctx.knobs.fuse_pf;
-  return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT, cs.m_dhT,
-                                ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0}, ctx.geo, ctx.geo.B, f, st, seg2_act, seg2_w,
-                                seg2_kblocks);
+  return launch_dgradT_fused<E>(ctx, ctx.m_dz128b[buf], cs.m_wdT, cs.with_x ? cs.m_dxT : cs.m_dhT,
+                                state16 ? cs.m_dhT16 : cs.m_dhT, ConvSeg{4 * HP / 64, cs.g.kh, cs.g.kw, 0}, ctx.geo,
+                                ctx.geo.B, f, st, seg2_act, seg2_w, seg2_kblocks, state16);
 }
 
 // Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
@@ -1559,6 +1576,13 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       if (hybrid_units < 1 || hybrid_units >= units) hybrid_units = 0;
     }
     if (hybrid_units > 0) bias_rows = kBiasRowsMax;
+    // 16-bit recurrent gradient states (dc, own dh_prev): every dgrad of this schedule is the worker-warp fused kernel
+    // (each op but the last is fused into the next one, the last one's dgrad is not needed), the only other writer /
+    // reader of dc is the stand-alone gate gradient of the very first op
+    bool state16 = ctx.knobs.state16 && ctx.knobs.recomp_c && ctx.knobs.fuse_workers == 2 && fused2_ok(ctx) &&
+                   hybrid_units == 0 && std::is_same<E, __half>::value;
+    for (int k = 0; k < ncell && state16; ++k)
+      if (p->cells[k].with_x ? p->cells[k].g.CIP != 64 : k != 0) state16 = false;
     for (int k = 0; k < ncell; ++k)
       CU_TRY(cudaMemsetAsync(p->cells[k].bpart, 0,
                              static_cast<size_t>(hybrid_units > 0 ? kBiasRowsMax : kGateGradBlocks) * 4 * HP * 4, st));
@@ -1576,7 +1600,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
         const float* c_prev = (o.t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, o.t)) * npix * HP;
         const float* c_next = cs.c + static_cast<size_t>(cslot(cs, o.t + 1)) * npix * HP;
         const float* own = (o.t == cs.T - 1) ? nullptr : cs.dh_own;
-        RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b));
+        if (state16 && n != 0) return fail(CLSTM_EINVAL, "backward schedule: an unfused step inside the 16-bit-state chain");
+        RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b, state16));
       }
       gate_done = false;
       bool fused_here = false;
@@ -1614,15 +1639,19 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
           }
           if (head_in_gemm)
             RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nullptr, nx.e2, b, st, fuse_units, &p->m_G128,
-                                       &p->m_whdT, p->KG / 64));
+                                       &p->m_whdT, p->KG / 64, state16));
           else
-            RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nx.e1, nx.e2, b, st, fuse_units));
+            RC_TRY(cell_dgrad_fused<E>(ctx, cs, cn, nx.t, own_n, nx.e1, nx.e2, b, st, fuse_units, nullptr, nullptr, 0,
+                                       state16));
           fused_here = true;
           gate_done = true;
         }
       }
       // the bottom cell's step 0 has nobody to hand a gradient to: its dgrad would only produce d(initial h) = unused
-      if (!fused_here && (cs.with_x || o.t > 0)) RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      if (!fused_here && (cs.with_x || o.t > 0)) {
+        if (state16) return fail(CLSTM_EINVAL, "backward schedule: a plain dgrad inside the 16-bit-state chain");
+        RC_TRY(cell_dgrad<E>(ctx, cs, st, b));
+      }
       RC_TRY(cell_wgrad<E>(ctx, cs, in, hslot(cs, o.t), first, st, b, gwp));
       if (fused_here) b ^= 1;
     }

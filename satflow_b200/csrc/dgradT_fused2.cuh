@@ -31,7 +31,10 @@ inline size_t dgradTf2_smem_bytes(int stages) {
 }
 
 // RC: c' of the consumer step is recomputed from its saved gates and c_prev instead of being read (gate_grad_item4).
-template <typename E, int WSETS, bool RC = false>
+// S16: the recurrent gradient states live in HBM as 16-bit values times kStateDown (ptx.cuh): the producing cell's dh_prev
+// (tmX1 is then a 16-bit map) and the consumer's dc and own dh (f.dc / f.src0 point at E arrays) — half the bytes of four
+// of the launch's streams; every sum and the dc recurrence itself stay fp32 in registers.
+template <typename E, int WSETS, bool RC = false, bool S16 = false>
 __global__ void __launch_bounds__(kDf2Threads, 1)
 dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmG,
@@ -209,16 +212,25 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        float* dst = stg + (cl >> 6) * (32 * 64) + (cl & 63);
+        if (S16 && (cl >> 6) == f.h_block) {  // dh_prev: [32 px][64 ch] 16-bit in the first half of its block
+          E* dst = reinterpret_cast<E*>(stg + f.h_block * (32 * 64)) + (cl & 63);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j * 64] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) dst[j * 64] = Elem<E>::from_float(__uint_as_float(v[j]) * kStateDown);
+        } else {
+          float* dst = stg + (cl >> 6) * (32 * 64) + (cl & 63);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j * 64] = __uint_as_float(v[j]);
+        }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (issuer) {
 #pragma unroll
           for (int s2 = 0; s2 < 2; ++s2) {  // dh_prev of the producing cell (64 channels), 16-pixel boxes
             const int px = g * 32 + s2 * 16;
-            tma_store_4d(&tmX1, stg + f.h_block * (32 * 64) + s2 * 16 * 64, 0, w0 + (px & (p.BW - 1)), h0 + (px >> p.lbw), b);
+            const float* hb = stg + f.h_block * (32 * 64);
+            const void* src = S16 ? static_cast<const void*>(reinterpret_cast<const E*>(hb) + s2 * 16 * 64)
+                                  : static_cast<const void*>(hb + s2 * 16 * 64);
+            tma_store_4d(&tmX1, src, 0, w0 + (px & (p.BW - 1)), h0 + (px >> p.lbw), b);
           }
           tma_store_commit();
           mbar_arrive(&stg_full[team * 2 + bsel]);  // ordered after every drain thread's writes by the barrier above
@@ -255,6 +267,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
     struct Raw {
       uint2 g[4];
       float4 cp, cn, dc, s0, s1;
+      uint2 dc16, s016;  // S16: the packed forms of dc / s0
       unsigned pix;  // global pixel index, or 0xFFFFFFFF for an item outside the image / past the last unit
     };
     struct TileBase {
@@ -287,8 +300,13 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       r.g[3] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 192));
       r.cp = cp_c ? __ldg(reinterpret_cast<const float4*>(cp_c + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (!RC) r.cn = __ldg(reinterpret_cast<const float4*>(cn_c + o1));
-      r.dc = *reinterpret_cast<const float4*>(dc_c + o1);  // read and written by this thread only
-      if (s0_c) r.s0 = __ldg(reinterpret_cast<const float4*>(s0_c + o1));
+      if constexpr (S16) {
+        r.dc16 = *reinterpret_cast<const uint2*>(reinterpret_cast<const E*>(f.dc) + chunk * 4 + o1);
+        if (s0_c) r.s016 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const E*>(f.src0) + chunk * 4 + o1));
+      } else {
+        r.dc = *reinterpret_cast<const float4*>(dc_c + o1);  // read and written by this thread only
+        if (s0_c) r.s0 = __ldg(reinterpret_cast<const float4*>(s0_c + o1));
+      }
       if (s1_c) r.s1 = __ldg(reinterpret_cast<const float4*>(s1_c + o1));
     };
     auto consume = [&](const Raw& r, const float* stg, int s) {
@@ -298,13 +316,29 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
         const float4 a0 = *reinterpret_cast<const float4*>(stg + (s * 8 + pxl) * 64 + chunk * 4);
         dhv[0] = a0.x, dhv[1] = a0.y, dhv[2] = a0.z, dhv[3] = a0.w;
       }
-      if (s0_c) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
+      float4 dcin;
+      if constexpr (S16) {
+        const float2 a = Elem<E>::unpack2(r.dc16.x), b2 = Elem<E>::unpack2(r.dc16.y);
+        dcin = make_float4(a.x * kStateUp, a.y * kStateUp, b2.x * kStateUp, b2.y * kStateUp);
+        if (s0_c) {
+          const float2 c0 = Elem<E>::unpack2(r.s016.x), c1 = Elem<E>::unpack2(r.s016.y);
+          dhv[0] = fmaf(c0.x, kStateUp, dhv[0]), dhv[1] = fmaf(c0.y, kStateUp, dhv[1]);
+          dhv[2] = fmaf(c1.x, kStateUp, dhv[2]), dhv[3] = fmaf(c1.y, kStateUp, dhv[3]);
+        }
+      } else {
+        dcin = r.dc;
+        if (s0_c) dhv[0] += r.s0.x, dhv[1] += r.s0.y, dhv[2] += r.s0.z, dhv[3] += r.s0.w;
+      }
       if (s1_c) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
       float4 dcn;
       uint2 dzp[4];
-      gate_grad_item4<E, RC>(r.g, r.cp, r.cn, r.dc, dhv, bsum, zmax, dcn, dzp);
+      gate_grad_item4<E, RC>(r.g, r.cp, r.cn, dcin, dhv, bsum, zmax, dcn, dzp);
       const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;
-      *reinterpret_cast<float4*>(dc_c + o1) = dcn;
+      if constexpr (S16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<E*>(f.dc) + chunk * 4 + o1) =
+            make_uint2(Elem<E>::pack2(dcn.x * kStateDown, dcn.y * kStateDown), Elem<E>::pack2(dcn.z * kStateDown, dcn.w * kStateDown));
+      else
+        *reinterpret_cast<float4*>(dc_c + o1) = dcn;
 #pragma unroll
       for (int a = 0; a < 4; ++a) *reinterpret_cast<uint2*>(dzo_c + o4 + a * 64) = dzp[a];
     };

@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(256)
 gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
                  const float* __restrict__ dh0, const float* __restrict__ dh1, const float* __restrict__ dh2,
                  float* __restrict__ dc, E* __restrict__ dz, float* __restrict__ bias_partial, int bias_accumulate,
-                 size_t npix, int HP, unsigned int* __restrict__ dz_absmax) {
+                 size_t npix, int HP, unsigned int* __restrict__ dz_absmax, int state16 = 0) {
+  // state16: dc and dh0 (the cell's own recurrent dh) are E arrays holding value * kStateDown (see ptx.cuh)
   extern __shared__ float red[];  // [256][9] padded
   uint32_t zmax = 0;  // packed running max |dz| of this thread (range statistics, see fold_absmax)
   const int groups = HP / 8;
@@ -408,12 +409,19 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
       for (int e = 0; e < 8; ++e) cp[e] = 0.f;
     }
     ld8(c_next, cn);
-    ld8(dc, dcv);
+    auto ld8h = [&](const float* src, float* out) {  // 8 packed 16-bit values times kStateDown
+      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const E*>(src) + off);
+      const float2 p0 = Elem<E>::unpack2(u.x), p1 = Elem<E>::unpack2(u.y), p2 = Elem<E>::unpack2(u.z),
+                   p3 = Elem<E>::unpack2(u.w);
+      out[0] = p0.x * kStateUp, out[1] = p0.y * kStateUp, out[2] = p1.x * kStateUp, out[3] = p1.y * kStateUp;
+      out[4] = p2.x * kStateUp, out[5] = p2.y * kStateUp, out[6] = p3.x * kStateUp, out[7] = p3.y * kStateUp;
+    };
+    if (state16) ld8h(dc, dcv); else ld8(dc, dcv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) dhv[e] = 0.f;
     float tmp[8];
     if (dh0) {
-      ld8(dh0, tmp);
+      if (state16) ld8h(dh0, tmp); else ld8(dh0, tmp);
 #pragma unroll
       for (int e = 0; e < 8; ++e) dhv[e] += tmp[e];
     }
@@ -442,8 +450,14 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
 #pragma unroll
       for (int a = 0; a < 4; ++a) bsum[a][e] += dzv[a][e];
     }
-    *reinterpret_cast<float4*>(dc + off) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-    *reinterpret_cast<float4*>(dc + off + 4) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+    if (state16) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<E*>(dc) + off) =
+          make_uint4(Elem<E>::pack2(dcn[0] * kStateDown, dcn[1] * kStateDown), Elem<E>::pack2(dcn[2] * kStateDown, dcn[3] * kStateDown),
+                     Elem<E>::pack2(dcn[4] * kStateDown, dcn[5] * kStateDown), Elem<E>::pack2(dcn[6] * kStateDown, dcn[7] * kStateDown));
+    } else {
+      *reinterpret_cast<float4*>(dc + off) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+      *reinterpret_cast<float4*>(dc + off + 4) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const uint4 o = make_uint4(Elem<E>::pack2(dzv[a][0], dzv[a][1]), Elem<E>::pack2(dzv[a][2], dzv[a][3]),
