@@ -571,10 +571,12 @@ def run_ours(args):
         gg_bytes = npix * hid * (4 * 2 + 4 + 4 + 2 * 4 + 2 * 4 + 4 * 2)  # gates, c_prev, c_next, 2 dh, dc r/w, dz
         # algorithmic bytes per launch (16-bit x / h / gates / dz, fp32 c / dc / dh; weights negligible)
         px = npix * hid
-        by_cell = px * (2 + 2 + 4 + 2 + 4 + 8)            # x, h_prev, c_prev read; h, c, 4 gates written
+        c16 = args.dtype == "fp16" and os.environ.get("CLSTM_C16", "1") != "0"   # c crosses HBM in 16 bits
+        cb = 2 if c16 else 4
+        by_cell = px * (2 + 2 + cb + 2 + cb + 8)          # x, h_prev, c_prev read; h, c, 4 gates written
         rc = args.dtype == "fp16" and os.environ.get("CLSTM_RECOMP_C", "1") != "0"
         s16 = rc and os.environ.get("CLSTM_STATE16", "1") != "0"   # dh_prev / own dh / dc in 16 bits
-        by_fused = px * (8 + (2 if s16 else 4) + 8 + 4 + (0 if rc else 4) + (2 if s16 else 4) + (4 if s16 else 8) + 8)  # dz read, dh_prev written; gates, c_prev, (c_next
+        by_fused = px * (8 + (2 if s16 else 4) + 8 + cb + (0 if rc else cb) + (2 if s16 else 4) + (4 if s16 else 8) + 8)  # dz read, dh_prev written; gates, c_prev, (c_next
                                                            # unless it is recomputed from the gates), ONE dh source from HBM
                                                            # (the other is this launch's dx, in shared memory; with the head
                                                            # segment the head's G tile replaces dstack, same bytes), dc r/w,

@@ -247,7 +247,7 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     if (issuer && has_cprev && cluster_id < total_units) {
       int nt, w0, h0, b, kb;
       coords(cluster_id, nt, w0, h0, b, kb);
-      mbar_expect_tx(&cprev_full[half], 8192);
+      mbar_expect_tx(&cprev_full[half], p.c16 ? 4096 : 8192);
       tma_load_4d(stg + kStgCprev, &tmX3, &cprev_full[half], nt * 64 + half * 32, w0, h0, b + p.cprev_boff);
     }
     for (int unit = cluster_id; unit < total_units; unit += n_clusters) {
@@ -269,10 +269,22 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         if (has_cprev) {
           mbar_wait(&cprev_full[half], cp_phase);
           cp_phase ^= 1;
+          if (p.c16) {
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            const float4 t = *reinterpret_cast<const float4*>(stg + kStgCprev + r * 64 + ((j ^ x64) << 4));
-            cp[4 * j + 0] = t.x, cp[4 * j + 1] = t.y, cp[4 * j + 2] = t.z, cp[4 * j + 3] = t.w;
+            for (uint32_t j = 0; j < 2; ++j) {  // 32-byte rows, SWIZZLE_32B (like h)
+              const uint4 t = *reinterpret_cast<const uint4*>(stg + kStgCprev + r * 32 + ((j ^ x32) << 4));
+              const float2 a0 = Elem<E>::unpack2(t.x), a1 = Elem<E>::unpack2(t.y), a2 = Elem<E>::unpack2(t.z),
+                           a3 = Elem<E>::unpack2(t.w);
+              cp[8 * j + 0] = a0.x * kCScaleInv, cp[8 * j + 1] = a0.y * kCScaleInv, cp[8 * j + 2] = a1.x * kCScaleInv;
+              cp[8 * j + 3] = a1.y * kCScaleInv, cp[8 * j + 4] = a2.x * kCScaleInv, cp[8 * j + 5] = a2.y * kCScaleInv;
+              cp[8 * j + 6] = a3.x * kCScaleInv, cp[8 * j + 7] = a3.y * kCScaleInv;
+            }
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+              const float4 t = *reinterpret_cast<const float4*>(stg + kStgCprev + r * 64 + ((j ^ x64) << 4));
+              cp[4 * j + 0] = t.x, cp[4 * j + 1] = t.y, cp[4 * j + 2] = t.z, cp[4 * j + 3] = t.w;
+            }
           }
         } else {
 #pragma unroll
@@ -288,7 +300,7 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
             if (un < total_units) coords(un, ntn, w0n, h0n, bn, kbn);
           }
           if (un < total_units) {
-            mbar_expect_tx(&cprev_full[half], 8192);
+            mbar_expect_tx(&cprev_full[half], p.c16 ? 4096 : 8192);
             tma_load_4d(stg + kStgCprev, &tmX3, &cprev_full[half], ntn * 64 + j0n, w0n, h0n, bn + p.cprev_boff);
           }
         }
@@ -314,14 +326,23 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(empty_remote + acc * 8);
         }
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(stg + kStgC + r * 64 + ((j ^ x64) << 4)) =
-              make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
         auto pack8 = [](const float* v) {
           return make_uint4(Elem<E>::pack2(v[0], v[1]), Elem<E>::pack2(v[2], v[3]), Elem<E>::pack2(v[4], v[5]),
                             Elem<E>::pack2(v[6], v[7]));
         };
+        if (p.c16) {
+          float cs16[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cs16[e] = cn[e] * kCScale;
+#pragma unroll
+          for (uint32_t j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(stg + kStgC + r * 32 + ((j ^ x32) << 4)) = pack8(cs16 + 8 * j);
+        } else {
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(stg + kStgC + r * 64 + ((j ^ x64) << 4)) =
+                make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+        }
 #pragma unroll
         for (uint32_t j = 0; j < 2; ++j)
           *reinterpret_cast<uint4*>(stg + kStgH + r * 32 + ((j ^ x32) << 4)) = pack8(hn + 8 * j);

@@ -122,6 +122,7 @@ struct Knobs {
                             // launch whose epilogue runs the top decoder cell's gate gradient of step t (no dstack)
   int state16 = 1;          // CLSTM_STATE16: dc and the cells' own dh_prev in 16 bits (at the dz scale) between the launches of the fused
                             // backward chain (fp16 operands, worker-warp fused dgrad with recomputed c' only)
+  int c16 = 1;              // CLSTM_C16: the cell state c crosses HBM in 16 bits (x 2^8) in big (non-persistent) fp16 rollouts
   int pair = 1;             // CLSTM_PAIR: cell step on CTA pairs (cta_group::2, cellstep_pair.cuh) for shapes with at least two
                             // waves of tiles
   int persist = 1;          // CLSTM_PERSIST: one persistent launch for the whole forward chain when the state fits on chip
@@ -148,6 +149,7 @@ struct Knobs {
     recomp_c = env_int("CLSTM_RECOMP_C", recomp_c);
     head_fuse = env_int("CLSTM_HEAD_FUSE", head_fuse);
     state16 = env_int("CLSTM_STATE16", state16);
+    c16 = env_int("CLSTM_C16", c16);
     pair = env_int("CLSTM_PAIR", pair);
     persist = env_int("CLSTM_PERSIST", persist);
     graph = env_int("CLSTM_GRAPH", graph);
@@ -412,6 +414,7 @@ struct Ctx {
   int HP = 0;
   int training = 0;
   float grad_scale = 0.f;
+  bool c16 = false;        // rollout plans: the c stacks hold E values times kCScale (CLSTM_C16), see decide_c16
   void* dz = nullptr;      // E [npix][4HP]  (buffer 0; == dzb[0])
   void* dzb[2] = {nullptr, nullptr};  // two dz buffers: gate-grad of step n+1 overlaps the wgrad of step n
   float* scale = nullptr;  // device {S, 1/S}
@@ -545,8 +548,8 @@ int map_cell(CellState& cs, const Ctx& ctx) {
   RC_TRY(make_map_w(&cs.m_wp128, ctx.dtype, cs.wp, cs.Kf, 4 * ctx.HP, 128));
   if (ctx.training)
     RC_TRY(make_map_w(&cs.m_wd, ctx.dtype, cs.wd, cs.Kd, cs.rows_d, cs.n_tile_d));
-  RC_TRY(make_map_epi(&cs.m_c16, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW,
-                      g.BH));
+  RC_TRY(make_map_epi(&cs.m_c16, ctx.c16 ? 2 : 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H,
+                      static_cast<long long>(cs.slots_c) * g.B, g.BW, g.BH));
   RC_TRY(make_map_epi(&cs.m_h16, 2, ctx.dtype, cs.h, ctx.HP, g.W, g.H, imgs, g.BW, g.BH));
   RC_TRY(make_map_epi(&cs.m_c8, 4, ctx.dtype, cs.c, ctx.HP, g.W, g.H, static_cast<long long>(cs.slots_c) * g.B, g.BW, g.BH,
                       8));
@@ -728,6 +731,7 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
       }
       // c' recomputed from the saved gates: 11-bit (fp16) gates only, see gate_grad_item4
       const bool rc = cx.knobs.recomp_c && std::is_same<E, __half>::value;
+      if (f.c16 && !rc) return fail(CLSTM_EINVAL, "dgradT_fused: a 16-bit c stack needs CLSTM_RECOMP_C=1");
       if (state16) {
         if (!rc || cx.knobs.fuse_workers != 2)
           return fail(CLSTM_EINVAL, "dgradT_fused: 16-bit states need CLSTM_FUSE_WORKERS=2 and CLSTM_RECOMP_C=1");
@@ -741,7 +745,7 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
       return after_launch(seg2_kblocks ? "dgradT_fused2_kernel[+head dgrad]" : "dgradT_fused2_kernel");
     }
   }
-  if (seg2_kblocks || state16)
+  if (seg2_kblocks || state16 || f.c16)
     return fail(CLSTM_EINVAL, "dgradT_fused: the second K segment / 16-bit states need the worker-warp kernel");
   static bool attr_set = false;
   if (!attr_set) {
@@ -892,6 +896,7 @@ int cell_forward_step(const Ctx& ctx, CellState& cs, const InputRef& in, int sp,
   p.h_next = static_cast<E*>(cs.h) + static_cast<size_t>(sn) * cs.h_slot_elems(ctx.geo);
   p.gates = gates;
   p.ldc = ctx.HP;
+  p.c16 = ctx.c16 ? 1 : 0;  // only plans whose every cell step takes the staged epilogue below set it (decide_c16)
   if (cnext_slot >= 0) {  // staged epilogue: image offsets into the c / h / gates stacks
     p.cprev_boff = (c_prev != nullptr && cprev_slot >= 0) ? cprev_slot * ctx.geo.B : -1;
     p.cnext_boff = cnext_slot * ctx.geo.B;
@@ -924,7 +929,7 @@ int cell_gate_grad(const Ctx& ctx, CellState& cs, const void* gates, const float
   // two kernels still did not overlap: DESIGN.md "backward overlap".)
   gate_grad_kernel<E><<<kGateGradBlocks, 256, 256 * 9 * sizeof(float), st>>>(
       static_cast<const E*>(gates), c_prev, c_next, dh0, dh1, dh2, cs.dc, static_cast<E*>(ctx.dzb[buf]), cs.bpart,
-      !first, ctx.geo.npix(), ctx.HP, ctx.amax + 1, state16 ? 1 : 0);
+      !first, ctx.geo.npix(), ctx.HP, ctx.amax + 1, state16 ? 1 : 0, ctx.c16 ? 1 : 0);
   return after_launch("gate_grad_kernel");
 }
 
@@ -958,6 +963,12 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
 // slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
 inline int hslot(const CellState& cs, int s) { return s % cs.slots_h; }
 inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
+// Address of slot `slot` of a cell's c stack: fp32 [npix][HP], or E [npix][HP] times kCScale when ctx.c16 (the stack keeps
+// its fp32-sized allocation; the typed pointer is only a handle for the kernels, which know the format).
+inline float* cptr(const Ctx& ctx, const CellState& cs, int slot) {
+  const size_t slot_floats = ctx.geo.npix() * ctx.HP / (ctx.c16 ? 2 : 1);
+  return cs.c + static_cast<size_t>(slot) * slot_floats;
+}
 
 // dgrad of `cs` (reading dz[buf]) with the gate gradient of the NEXT step of the backward chain — cell `cn`, time
 // step `nt`, dh sources own / e1 / e2 — fused into its epilogue (dgradT.cuh); that gate gradient lands in dz[buf^1].
@@ -972,8 +983,9 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
   GateFuse f;
   memset(&f, 0, sizeof(f));
   f.gates = static_cast<const E*>(cn.gates) + static_cast<size_t>(nt) * npix * 4 * HP;
-  f.c_prev = (nt == 0) ? nullptr : cn.c + static_cast<size_t>(cslot(cn, nt)) * npix * HP;
-  f.c_next = cn.c + static_cast<size_t>(cslot(cn, nt + 1)) * npix * HP;
+  f.c_prev = (nt == 0) ? nullptr : cptr(ctx, cn, cslot(cn, nt));
+  f.c_next = cptr(ctx, cn, cslot(cn, nt + 1));
+  f.c16 = ctx.c16 ? 1 : 0;
   const float* srcs[3] = {own, e1, e2};
   for (const float*& sp : srcs)
     if (sp != nullptr && cs.with_x && sp == cs.dxb) {
@@ -1181,7 +1193,7 @@ int persist_setup(clstm_plan* p, cudaStream_t st) {
   p->persist_ok = false;
   const int n_tiles = ctx.HP / 64;
   const long long tiles = static_cast<long long>(geo.B) * geo.tiles_w * geo.tiles_h * n_tiles;
-  if (!ctx.knobs.persist || !ctx.knobs.staged || p->ncell > kPersistMaxCells || tiles > ctx.dev.sms) return 0;
+  if (!ctx.knobs.persist || !ctx.knobs.staged || p->ncell > kPersistMaxCells || tiles > ctx.dev.sms || ctx.c16) return 0;
   if (1 + 5 * p->ncell > kPersistMaxMaps) return 0;
   for (int k = 0; k < p->ncell; ++k)
     if (p->cells[k].Kf / 64 > kKtabMax) return 0;
@@ -1331,8 +1343,8 @@ int plan_forward(clstm_plan* p, const float* x, float* y, cudaStream_t st, int c
   auto step = [&](int k, int t) -> int {
     CellState& cs = p->cells[k];
     const InputRef in = plan_input(p, k, t);
-    const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
-    float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
+    const float* c_prev = (t == 0) ? nullptr : cptr(ctx, cs, cslot(cs, t));
+    float* c_next = cptr(ctx, cs, cslot(cs, t + 1));
     void* gates = c.training ? static_cast<void*>(static_cast<E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP)
                              : nullptr;
     return cell_forward_step<E>(ctx, cs, in, hslot(cs, t), hslot(cs, t + 1), c_prev, c_next, gates, st, cslot(cs, t),
@@ -1435,8 +1447,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     CellState& cs = p->cells[k];
     const InputRef in = plan_input(p, k, t);
     const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(t) * npix * 4 * HP;
-    const float* c_prev = (t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, t)) * npix * HP;
-    const float* c_next = cs.c + static_cast<size_t>(cslot(cs, t + 1)) * npix * HP;
+    const float* c_prev = (t == 0) ? nullptr : cptr(ctx, cs, cslot(cs, t));
+    const float* c_next = cptr(ctx, cs, cslot(cs, t + 1));
     const float* own = (t == cs.T - 1) ? nullptr : cs.dh_own;
     if (!overlap)
       return cell_backward_step<E>(ctx, cs, in, hslot(cs, t), gates, c_prev, c_next, own, e1, e2, st,
@@ -1536,8 +1548,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       if (!gate_done) {
         if (o.head) RC_TRY(head_back(o.t));
         const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(o.t) * npix * 4 * HP;
-        const float* c_prev = (o.t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, o.t)) * npix * HP;
-        const float* c_next = cs.c + static_cast<size_t>(cslot(cs, o.t + 1)) * npix * HP;
+        const float* c_prev = (o.t == 0) ? nullptr : cptr(ctx, cs, cslot(cs, o.t));
+        const float* c_next = cptr(ctx, cs, cslot(cs, o.t + 1));
         const float* own = (o.t == cs.T - 1) ? nullptr : cs.dh_own;
         RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b));
       }
@@ -1597,8 +1609,8 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
       if (!gate_done) {
         if (o.head) RC_TRY(head_back(o.t));
         const E* gates = static_cast<const E*>(cs.gates) + static_cast<size_t>(o.t) * npix * 4 * HP;
-        const float* c_prev = (o.t == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, o.t)) * npix * HP;
-        const float* c_next = cs.c + static_cast<size_t>(cslot(cs, o.t + 1)) * npix * HP;
+        const float* c_prev = (o.t == 0) ? nullptr : cptr(ctx, cs, cslot(cs, o.t));
+        const float* c_next = cptr(ctx, cs, cslot(cs, o.t + 1));
         const float* own = (o.t == cs.T - 1) ? nullptr : cs.dh_own;
         if (state16 && n != 0) return fail(CLSTM_EINVAL, "backward schedule: an unfused step inside the 16-bit-state chain");
         RC_TRY(cell_gate_grad<E>(ctx, cs, gates, c_prev, c_next, own, o.e1, o.e2, 0, st, b, state16));
@@ -1693,9 +1705,13 @@ int plan_read_state(clstm_plan* p, int cell, int step, float* h_out, float* c_ou
     if (step == 0) {
       CU_TRY(cudaMemsetAsync(c_out, 0, static_cast<size_t>(c.batch) * c.hidden * c.height * c.width * 4, st));
     } else {
-      const float* src = cs.c + static_cast<size_t>(cslot(cs, step)) * npix * HP;
-      unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(src, c_out, c.batch, c.hidden, c.height, c.width, HP,
-                                                             nullptr, 0);
+      const float* src = cptr(p->ctx, cs, cslot(cs, step));
+      if (p->ctx.c16)
+        unpack_nchw_kernel<E><<<kPackBlocks, 256, 0, st>>>(reinterpret_cast<const E*>(src), c_out, c.batch, c.hidden,
+                                                           c.height, c.width, HP, nullptr, 0, kCScaleInv);
+      else
+        unpack_nchw_kernel<float><<<kPackBlocks, 256, 0, st>>>(src, c_out, c.batch, c.hidden, c.height, c.width, HP,
+                                                               nullptr, 0);
       RC_TRY(after_launch("unpack_nchw_kernel"));
     }
   }
@@ -2012,6 +2028,18 @@ int clstm_plan_create(const clstm_config_t* cfg, clstm_plan_t** out) {
   ctx.grad_scale = cfg->grad_scale;
   p->L = cfg->n_layers;
   p->ncell = 2 * cfg->n_layers;
+  {
+    // 16-bit c stacks (ptx.cuh kCScale): big fp16 rollouts whose every cell step takes the staged TMA epilogue (not the
+    // persistent chain, which keeps c in TMEM and streams it out as fp32) and whose backward reads c through kernels
+    // that know the format: the stand-alone gate gradient, or the worker-warp fused dgrad with c' recomputed.
+    const Knobs& k = ctx.knobs;
+    const long long tiles = static_cast<long long>(ctx.geo.B) * ctx.geo.tiles_w * ctx.geo.tiles_h * (ctx.HP / 64);
+    const int sms = ctx.dev.sms > 0 ? ctx.dev.sms : 148;
+    const bool fused_chain = k.fuse_gate && k.dgradT && ctx.HP == 64 && cfg->n_layers >= 2 && !k.overlap;
+    ctx.c16 = k.c16 && cfg->dtype == CLSTM_F16 && k.staged == 1 && cfg->t_in <= kC16MaxSteps &&
+              cfg->t_out <= kC16MaxSteps && tiles > sms && !k.wg_gate && k.hybrid_pct == 0 &&
+              (!cfg->training || !fused_chain || (k.recomp_c && k.fuse_workers == 2));
+  }
   p->KX = round_up(cfg->kernel_h * cfg->kernel_w * cfg->in_channels, 64);
   p->KG = round_up(9 * cfg->out_channels, 128);
   p->NT = round_up(cfg->out_channels, 16);
@@ -2216,8 +2244,8 @@ int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, voi
   const size_t npix = p->ctx.geo.npix();
   const int HP = p->ctx.HP;
   const InputRef in = plan_input(p, cell, step);
-  const float* c_prev = (step == 0) ? nullptr : cs.c + static_cast<size_t>(cslot(cs, step)) * npix * HP;
-  float* c_next = cs.c + static_cast<size_t>(cslot(cs, step + 1)) * npix * HP;
+  const float* c_prev = (step == 0) ? nullptr : cptr(p->ctx, cs, cslot(cs, step));
+  float* c_next = cptr(p->ctx, cs, cslot(cs, step + 1));
   void* gates = nullptr;
   if (p->cfg.training) gates = static_cast<uint8_t*>(cs.gates) + static_cast<size_t>(step) * npix * 4 * HP * 2;
   switch (kind) {

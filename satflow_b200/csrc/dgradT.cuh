@@ -252,6 +252,7 @@ struct GateFuse {
   float* bias_partial;   // [gridDim.x][4*HP], accumulated
   unsigned int* dz_absmax;  // range statistics of the 16-bit dz this pass writes (float bits, see fold_absmax)
   int HP;
+  int c16;               // 1: c_prev (and c_next) are E arrays holding c * kCScale (CLSTM_C16; worker-warp kernel only)
   int fuse_units;        // hybrid schedule: only units < fuse_units run the gate gradient here; for the others the dx
                          // block is written to HBM (tmX0) and the worker warps of the following wgrad launch finish
                          // the job (clstm.cu "hybrid").  INT_MAX = everything here.

@@ -268,6 +268,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       uint2 g[4];
       float4 cp, cn, dc, s0, s1;
       uint2 dc16, s016;  // S16: the packed forms of dc / s0
+      uint2 cp16;        // f.c16: the packed form of c_prev
       unsigned pix;  // global pixel index, or 0xFFFFFFFF for an item outside the image / past the last unit
     };
     struct TileBase {
@@ -298,7 +299,11 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       r.g[1] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 64));
       r.g[2] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 128));
       r.g[3] = __ldg(reinterpret_cast<const uint2*>(gates_c + o4 + 192));
-      r.cp = cp_c ? __ldg(reinterpret_cast<const float4*>(cp_c + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f.c16)
+        r.cp16 = f.c_prev ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const E*>(f.c_prev) + chunk * 4 + o1))
+                          : make_uint2(0u, 0u);
+      else
+        r.cp = cp_c ? __ldg(reinterpret_cast<const float4*>(cp_c + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (!RC) r.cn = __ldg(reinterpret_cast<const float4*>(cn_c + o1));
       if constexpr (S16) {
         r.dc16 = *reinterpret_cast<const uint2*>(reinterpret_cast<const E*>(f.dc) + chunk * 4 + o1);
@@ -316,6 +321,11 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
         const float4 a0 = *reinterpret_cast<const float4*>(stg + (s * 8 + pxl) * 64 + chunk * 4);
         dhv[0] = a0.x, dhv[1] = a0.y, dhv[2] = a0.z, dhv[3] = a0.w;
       }
+      float4 cpv = r.cp;
+      if (f.c16) {
+        const float2 a = Elem<E>::unpack2(r.cp16.x), b2 = Elem<E>::unpack2(r.cp16.y);
+        cpv = make_float4(a.x * kCScaleInv, a.y * kCScaleInv, b2.x * kCScaleInv, b2.y * kCScaleInv);
+      }
       float4 dcin;
       if constexpr (S16) {
         const float2 a = Elem<E>::unpack2(r.dc16.x), b2 = Elem<E>::unpack2(r.dc16.y);
@@ -332,7 +342,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
       if (s1_c) dhv[0] += r.s1.x, dhv[1] += r.s1.y, dhv[2] += r.s1.z, dhv[3] += r.s1.w;
       float4 dcn;
       uint2 dzp[4];
-      gate_grad_item4<E, RC>(r.g, r.cp, r.cn, dcin, dhv, bsum, zmax, dcn, dzp);
+      gate_grad_item4<E, RC>(r.g, cpv, r.cn, dcin, dhv, bsum, zmax, dcn, dzp);
       const unsigned o4 = r.pix * (4 * 64), o1 = r.pix * 64;
       if constexpr (S16)
         *reinterpret_cast<uint2*>(reinterpret_cast<E*>(f.dc) + chunk * 4 + o1) =

@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(256)
 gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_next,
                  const float* __restrict__ dh0, const float* __restrict__ dh1, const float* __restrict__ dh2,
                  float* __restrict__ dc, E* __restrict__ dz, float* __restrict__ bias_partial, int bias_accumulate,
-                 size_t npix, int HP, unsigned int* __restrict__ dz_absmax, int state16 = 0) {
+                 size_t npix, int HP, unsigned int* __restrict__ dz_absmax, int state16 = 0, int c16 = 0) {
+  // c16: c_prev / c_next are E arrays holding c * kCScale
   // state16: dc and dh0 (the cell's own recurrent dh) are E arrays holding value * kStateDown (see ptx.cuh)
   extern __shared__ float red[];  // [256][9] padded
   uint32_t zmax = 0;  // packed running max |dz| of this thread (range statistics, see fold_absmax)
@@ -402,26 +403,26 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
       const float4 b = *reinterpret_cast<const float4*>(src + off + 4);
       out[0] = a.x, out[1] = a.y, out[2] = a.z, out[3] = a.w, out[4] = b.x, out[5] = b.y, out[6] = b.z, out[7] = b.w;
     };
+    auto ld8h = [&](const float* src, float* out, float up) {  // 8 packed 16-bit values times a power of two
+      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const E*>(src) + off);
+      const float2 p0 = Elem<E>::unpack2(u.x), p1 = Elem<E>::unpack2(u.y), p2 = Elem<E>::unpack2(u.z),
+                   p3 = Elem<E>::unpack2(u.w);
+      out[0] = p0.x * up, out[1] = p0.y * up, out[2] = p1.x * up, out[3] = p1.y * up;
+      out[4] = p2.x * up, out[5] = p2.y * up, out[6] = p3.x * up, out[7] = p3.y * up;
+    };
     if (c_prev) {
-      ld8(c_prev, cp);
+      if (c16) ld8h(c_prev, cp, kCScaleInv); else ld8(c_prev, cp);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) cp[e] = 0.f;
     }
-    ld8(c_next, cn);
-    auto ld8h = [&](const float* src, float* out) {  // 8 packed 16-bit values times kStateDown
-      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const E*>(src) + off);
-      const float2 p0 = Elem<E>::unpack2(u.x), p1 = Elem<E>::unpack2(u.y), p2 = Elem<E>::unpack2(u.z),
-                   p3 = Elem<E>::unpack2(u.w);
-      out[0] = p0.x * kStateUp, out[1] = p0.y * kStateUp, out[2] = p1.x * kStateUp, out[3] = p1.y * kStateUp;
-      out[4] = p2.x * kStateUp, out[5] = p2.y * kStateUp, out[6] = p3.x * kStateUp, out[7] = p3.y * kStateUp;
-    };
-    if (state16) ld8h(dc, dcv); else ld8(dc, dcv);
+    if (c16) ld8h(c_next, cn, kCScaleInv); else ld8(c_next, cn);
+    if (state16) ld8h(dc, dcv, kStateUp); else ld8(dc, dcv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) dhv[e] = 0.f;
     float tmp[8];
     if (dh0) {
-      if (state16) ld8h(dh0, tmp); else ld8(dh0, tmp);
+      if (state16) ld8h(dh0, tmp, kStateUp); else ld8(dh0, tmp);
 #pragma unroll
       for (int e = 0; e < 8; ++e) dhv[e] += tmp[e];
     }

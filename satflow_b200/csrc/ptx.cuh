@@ -254,6 +254,12 @@ constexpr float kHScaleInv = 1.f / 4096.f;
 // head-room as dz and need no shift; their small end sits 2-3 bits ABOVE dz's (dz = dh * o(1-o) * ...), and a down-shift
 // only pushes the vanishing gradients of the bottom cells into fp16's subnormals (a 2^-6 shift doubled the error of the
 // 3-layer 5x5 sweep case).  Kept as named constants: a power of two here is exact and free.
+// 16-bit cell state (CLSTM_C16): c crosses HBM as c * 2^8.  |c_t| <= t (every step adds |i g| < 1), so 200 steps stay
+// below 65504 / 256; the smallest normal becomes 2.4e-7, which keeps the |c| ~ 1e-5 of a freshly re-initialised network
+// (CloudGAN, see kHScale) at full 11-bit precision.
+constexpr float kCScale = 256.f;
+constexpr float kCScaleInv = 1.f / 256.f;
+constexpr int kC16MaxSteps = 200;
 constexpr float kStateDown = 1.f;
 constexpr float kStateUp = 1.f;
 
