@@ -7,6 +7,7 @@ R=${1:-r2}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu --durations=5 2>&1 | grep -v "^$" | cut -c1-2000 | tail -40 > gpurun_out/${R}_gpu_tests.log
 tail -3 gpurun_out/${R}_gpu_tests.log
+timeout 300 python tools/margin_case.py 1 12 24 12 64 12 256 256 2 3 > gpurun_out/${R}_margins_256px_depth36.log 2>&1; cat gpurun_out/${R}_margins_256px_depth36.log
 timeout 500 python bench.py 2>gpurun_out/${R}_bench_err.log > gpurun_out/${R}_bench_n1.json
 cut -c1-300 gpurun_out/${R}_bench_n1.json; tail -2 gpurun_out/${R}_bench_err.log
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
