@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gpu_checks as G
 r = G.rollout_case(2, 2, 2, 12, 64, 12, 256, 256)
 worst = sorted(r.items(), key=lambda kv: -kv[1])[:5]
