@@ -1006,6 +1006,14 @@ int cell_dgrad_fused(const Ctx& ctx, CellState& cs, CellState& cn, int nt, const
                                 ctx.geo.B, f, st, seg2_act, seg2_w, seg2_kblocks, state16);
 }
 
+// The 16-bit recurrent gradient states (CLSTM_STATE16) apply when every dgrad of the backward chain is the worker-warp
+// fused kernel with recomputed c' (see plan_backward): knobs and dtype part of the condition.
+template <typename E>
+inline bool state16_knobs_ok(const Ctx& ctx) {
+  return ctx.knobs.state16 && ctx.knobs.recomp_c && ctx.knobs.fuse_workers == 2 && fused2_ok(ctx) &&
+         std::is_same<E, __half>::value;
+}
+
 // Shapes the fused dgrad + gate-gradient kernel supports (hidden padded to 64, 32-bit element offsets).
 inline bool fuse_supported(const Ctx& ctx) {
   return ctx.HP == 64 && ctx.geo.BW >= 16 && ctx.geo.npix() * 4 * ctx.HP < (1ull << 32) && ctx.knobs.dgradT &&
@@ -1591,8 +1599,7 @@ int plan_backward(clstm_plan* p, const float* dy, const float* y, float* const* 
     // 16-bit recurrent gradient states (dc, own dh_prev): every dgrad of this schedule is the worker-warp fused kernel
     // (each op but the last is fused into the next one, the last one's dgrad is not needed), the only other writer /
     // reader of dc is the stand-alone gate gradient of the very first op
-    bool state16 = ctx.knobs.state16 && ctx.knobs.recomp_c && ctx.knobs.fuse_workers == 2 && fused2_ok(ctx) &&
-                   hybrid_units == 0 && std::is_same<E, __half>::value;
+    bool state16 = state16_knobs_ok<E>(ctx) && hybrid_units == 0;
     for (int k = 0; k < ncell && state16; ++k)
       if (p->cells[k].with_x ? p->cells[k].g.CIP != 64 : k != 0) state16 = false;
     for (int k = 0; k < ncell; ++k)
@@ -2291,7 +2298,10 @@ int clstm_plan_profile_kernel(clstm_plan_t* p, int kind, int cell, int step, voi
         return fail(CLSTM_EINVAL, "fused dgrad + gate-gradient is not available for this cell / shape");
       CellState& cn = p->cells[cell - 1];
       if (step >= cn.T) return fail(CLSTM_EINVAL, "step %d out of range for the consumer cell", step);
-#define CALL_(E) cell_dgrad_fused<E>(p->ctx, cs, cn, step, cn.dh_own, cs.dxb, nullptr, 0, st)
+      // the kernel variant the default backward schedule launches (timing only: it runs on whatever the last backward left)
+#define CALL_(E)                                                                                                \
+  cell_dgrad_fused<E>(p->ctx, cs, cn, step, cn.dh_own, cs.dxb, nullptr, 0, st, 0x7fffffff, nullptr, nullptr, 0, \
+                      state16_knobs_ok<E>(p->ctx) && p->ctx.knobs.hybrid_pct == 0 && p->L >= 2)
       return DISPATCH_E(p->cfg.dtype, CALL_);
 #undef CALL_
     }

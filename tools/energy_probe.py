@@ -85,8 +85,9 @@ def main():
     del src, dst
 
     px = B * HW * HW * hid
-    for kind, name, nbytes in (("cell_fwd", "fused cell step (training variant)", px * 22),
-                               ("dgrad_fused", "dgradT + fused gate gradient", px * 44),
+    # algorithmic bytes per launch with the default storage formats (16-bit c, dc, dh; c' recomputed): DESIGN.md §4
+    for kind, name, nbytes in (("cell_fwd", "fused cell step (training variant)", px * 18),
+                               ("dgrad_fused", "dgradT + fused gate gradient", px * 34),
                                ("dgrad", "dgradT alone", px * 16), ("wgrad", "wgrad (halo rows)", px * 12),
                                ("gate_grad", "gate gradient alone", px * 40)):
         try:
@@ -95,7 +96,7 @@ def main():
             print(json.dumps({"kernel": name, "error": str(e)[:120]}), flush=True)
             continue
         report(name, us, summ, flops=None if kind == "gate_grad" else fl, nbytes=nbytes)
-    out = os.path.join(ROOT, "gpurun_out", "r2c_energy_probe.json")
+    out = os.path.join(ROOT, "gpurun_out", os.environ.get("PROBE_OUT", "energy_probe.json"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:
         json.dump({"idle": idle, "rows": rows}, f, indent=1)
