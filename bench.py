@@ -669,6 +669,18 @@ def run_ours(args):
         flops_step = 3 * algorithmic_flops_fwd(B * n_micro, t_in, t_out, C, hid, Co, HW, HW)
         extra["step_tflops"] = flops_step * world / ms_step / 1e9
         extra["step_frac_of_sustained_peak"] = flops_step / ms_step / 1e9 / peaks["bf16_sustained"]
+        # Energy view (DESIGN.md §4 "board power"): every GEMM kernel of the step, like cuBLAS, runs at the board's power
+        # cap, so joules per step is what the step time follows.  Power = median of the nvidia-smi samples taken during
+        # the timed region on rank 0 (few samples: indicative; tools/energy_probe.py is the per-kernel measurement).
+        try:
+            pw = (clocks or {}).get("power_w_median")
+            if pw:
+                extra["energy"] = {"board_power_w_median": pw, "joule_per_step": pw * ms_step * 1e-3,
+                                   "pj_per_algorithmic_flop": pw * ms_step * 1e-3 / flops_step * 1e12,
+                                   "cublas_bf16_pj_per_flop_same_pool": 0.709,
+                                   "source": "clocks sampler; cuBLAS figure from profiles/r2c_energy_probe.json"}
+        except Exception:
+            pass
         try:
             st = model.model.check_gradients()
             if st:

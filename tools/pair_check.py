@@ -1,3 +1,4 @@
+"""Quick parity check of the CTA-pair cell step at sizes that select it (used while bringing cellstep_pair.cuh up)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gpu_checks as G
