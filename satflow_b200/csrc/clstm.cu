@@ -106,7 +106,8 @@ struct Knobs {
   int fuse_pf = 1;          // CLSTM_FUSE_PF: its L2 prefetch distance in groups
   int fuse_sets = 4;        // CLSTM_FUSE_SETS: register sets of loads in flight per epilogue thread (2; 4 = setmaxnreg)
   int fuse_workers = 2;     // CLSTM_FUSE_WORKERS: gate gradient on dedicated worker warps (dgradT_fused2.cuh) with this
-                            // many register sets of loads in flight (2 or 4); 0 = the epilogue warps do it themselves
+                            // 2 register sets of loads in flight (2); 0 = the epilogue warps do it themselves.  (A 4-set
+                            // variant spilled at 136 registers and measured 1196 us: removed.)
   int head_rows = 1;        // CLSTM_HEAD_ROWS: row-marching output head (0: implicit-GEMM head)
   int head_band = 32;       // CLSTM_HEAD_BAND: rows per band of the row-marching head
   int wg_halo = 1;          // CLSTM_WG_HALO: halo-row wgrad
@@ -685,7 +686,7 @@ int launch_dgradT(const Ctx& cx, const CUtensorMap& dz128, const CUtensorMap& wT
 
 // The worker-warp generation of the fused kernel (dgradT_fused2.cuh) is selected and fits in shared memory.
 inline bool fused2_ok(const Ctx& cx) {
-  return (cx.knobs.fuse_workers == 2 || cx.knobs.fuse_workers == 4) &&
+  return cx.knobs.fuse_workers == 2 &&
          (cx.dev.smem_optin - static_cast<int>(dgradTf2_smem_bytes(0))) / kDtStageBytes >= 2;
 }
 
@@ -724,7 +725,6 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
       static bool attr2_set = false;
       if (!attr2_set) {
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
-        CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         CU_TRY((cudaFuncSetAttribute(dgradT_fused2_kernel<E, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.smem_optin)));
         attr2_set = true;
@@ -733,12 +733,10 @@ int launch_dgradT_fused(const Ctx& cx, const CUtensorMap& dz128, const CUtensorM
       const bool rc = cx.knobs.recomp_c && std::is_same<E, __half>::value;
       if (f.c16 && !rc) return fail(CLSTM_EINVAL, "dgradT_fused: a 16-bit c stack needs CLSTM_RECOMP_C=1");
       if (state16) {
-        if (!rc || cx.knobs.fuse_workers != 2)
+        if (!rc)
           return fail(CLSTM_EINVAL, "dgradT_fused: 16-bit states need CLSTM_FUSE_WORKERS=2 and CLSTM_RECOMP_C=1");
         dgradT_fused2_kernel<E, 2, true, true><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
-      } else if (cx.knobs.fuse_workers == 4)
-        dgradT_fused2_kernel<E, 4><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
-      else if (rc)
+      } else if (rc)
         dgradT_fused2_kernel<E, 2, true><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);
       else
         dgradT_fused2_kernel<E, 2><<<grid, kDf2Threads, dgradTf2_smem_bytes(st2), st>>>(dz128, wT, x1, gA, gW, p, f);

@@ -34,11 +34,12 @@ inline size_t dgradTf2_smem_bytes(int stages) {
 // S16: the recurrent gradient states live in HBM as 16-bit values times kStateDown (ptx.cuh): the producing cell's dh_prev
 // (tmX1 is then a 16-bit map) and the consumer's dc and own dh (f.dc / f.src0 point at E arrays) — half the bytes of four
 // of the launch's streams; every sum and the dc recurrence itself stay fp32 in registers.
-template <typename E, int WSETS, bool RC = false, bool S16 = false>
+template <typename E, int WSETS, bool RC = false, bool S16 = false>  // WSETS == 2 (a 4-set variant spilled: removed)
 __global__ void __launch_bounds__(kDf2Threads, 1)
 dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmG,
                      const __grid_constant__ CUtensorMap tmW2, const DgradTParams p, const GateFuse f) {
+  static_assert(WSETS == 2, "the worker loop below is written for two register sets of loads in flight");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_stg = smem + p.stages * kDtStageBytes;           // [team][buffer][kDf2StgBuf]
@@ -356,7 +357,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
     TileBase tb_cur = tile_base(blockIdx.x), tb_next;
     Raw rs[WSETS];
 #pragma unroll
-    for (int i = 0; i < WSETS; ++i) issue(rs[i], tb_cur, 0, i);  // WSETS <= 4 items of group 0
+    for (int i = 0; i < WSETS; ++i) issue(rs[i], tb_cur, 0, i);  // the first items of group 0
     uint32_t gcount = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       tb_next = tile_base(unit + static_cast<int>(gridDim.x));
@@ -367,17 +368,7 @@ dgradT_fused2_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_cons
         const int ng = (g + 1) & 3;
         const TileBase& tbn = (g == 3) ? tb_next : tb_cur;
         mbar_wait(&stg_full[team * 2 + bsel], use & 1);  // this group's dx block is staged
-        if constexpr (WSETS == 4) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            consume(rs[s], stg, s);
-            if (s == 3) {  // last read of the staging buffer by this thread is done
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&stg_empty[team * 2 + bsel]);
-            }
-            issue(rs[s], tbn, ng, s);
-          }
-        } else {  // two sets: item s uses set s & 1, loads run two items ahead
+        {  // two sets: item s uses set s & 1, loads run two items ahead
           consume(rs[0], stg, 0);
           issue(rs[0], tb_cur, g, 2);
           consume(rs[1], stg, 1);
