@@ -348,6 +348,8 @@ cellstep_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           *reinterpret_cast<uint4*>(stg + kStgH + r * 32 + ((j ^ x32) << 4)) = pack8(hn + 8 * j);
         if (p.gates_boff >= 0) {
 #pragma unroll
+          for (int e = 0; e < 16; ++e) gi[e] -= kGateCenter, gf[e] -= kGateCenter, go[e] -= kGateCenter;  // stored centred
+#pragma unroll
           for (uint32_t j = 0; j < 2; ++j) {
             *reinterpret_cast<uint4*>(stg + kStgG + 0 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gi + 8 * j);
             *reinterpret_cast<uint4*>(stg + kStgG + 1 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gf + 8 * j);

@@ -154,10 +154,13 @@ __device__ __forceinline__ void convgemm_epilogue_tile(const ConvGemmParams& p, 
           for (int gt = 0; gt < 4; ++gt) {
             uint4* gd = reinterpret_cast<uint4*>(gbase + static_cast<size_t>(gt) * p.ldc);
             const float* gv = gsrc[gt];
+            const float ctr = gt < 3 ? kGateCenter : 0.f;  // sigmoid gates are stored centred (ptx.cuh kGateCenter)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              gd[e] = make_uint4(Elem<E>::pack2(gv[8 * e + 0], gv[8 * e + 1]), Elem<E>::pack2(gv[8 * e + 2], gv[8 * e + 3]),
-                                 Elem<E>::pack2(gv[8 * e + 4], gv[8 * e + 5]), Elem<E>::pack2(gv[8 * e + 6], gv[8 * e + 7]));
+              gd[e] = make_uint4(Elem<E>::pack2(gv[8 * e + 0] - ctr, gv[8 * e + 1] - ctr),
+                                 Elem<E>::pack2(gv[8 * e + 2] - ctr, gv[8 * e + 3] - ctr),
+                                 Elem<E>::pack2(gv[8 * e + 4] - ctr, gv[8 * e + 5] - ctr),
+                                 Elem<E>::pack2(gv[8 * e + 6] - ctr, gv[8 * e + 7] - ctr));
           }
         }
       }
@@ -470,6 +473,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
             *reinterpret_cast<uint4*>(stg + kStg8H + r * 16) = pack8(hn);
             if (p.gates_boff >= 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) gi[e] -= kGateCenter, gf[e] -= kGateCenter, go[e] -= kGateCenter;  // stored centred
               *reinterpret_cast<uint4*>(stg + kStg8G + 0 * 2048 + r * 16) = pack8(gi);
               *reinterpret_cast<uint4*>(stg + kStg8G + 1 * 2048 + r * 16) = pack8(gf);
               *reinterpret_cast<uint4*>(stg + kStg8G + 2 * 2048 + r * 16) = pack8(go);
@@ -599,6 +604,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (uint32_t j = 0; j < 2; ++j)
               *reinterpret_cast<uint4*>(stg + kStgH + r * 32 + ((j ^ x32) << 4)) = pack8(hn + 8 * j);
             if (p.gates_boff >= 0) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) gi[e] -= kGateCenter, gf[e] -= kGateCenter, go[e] -= kGateCenter;  // stored centred
 #pragma unroll
               for (uint32_t j = 0; j < 2; ++j) {
                 *reinterpret_cast<uint4*>(stg + kStgG + 0 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gi + 8 * j);

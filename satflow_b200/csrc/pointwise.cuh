@@ -394,8 +394,9 @@ gate_grad_kernel(const E* __restrict__ gates, const float* __restrict__ c_prev, 
       const uint4 u = *reinterpret_cast<const uint4*>(gates + pix * 4 * HP + a * HP + grp * 8);
       const float2 p0 = Elem<E>::unpack2(u.x), p1 = Elem<E>::unpack2(u.y), p2 = Elem<E>::unpack2(u.z),
                    p3 = Elem<E>::unpack2(u.w);
-      gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
-      gv[a][4] = p2.x, gv[a][5] = p2.y, gv[a][6] = p3.x, gv[a][7] = p3.y;
+      const float ctr = a < 3 ? kGateCenter : 0.f;  // sigmoid gates are stored centred (ptx.cuh kGateCenter)
+      gv[a][0] = p0.x + ctr, gv[a][1] = p0.y + ctr, gv[a][2] = p1.x + ctr, gv[a][3] = p1.y + ctr;
+      gv[a][4] = p2.x + ctr, gv[a][5] = p2.y + ctr, gv[a][6] = p3.x + ctr, gv[a][7] = p3.y + ctr;
     }
     float cp[8], cn[8], dhv[8], dcv[8];
     auto ld8 = [&](const float* src, float* out) {
@@ -504,7 +505,8 @@ __device__ __forceinline__ void gate_grad_item4(const uint2 (&g)[4], const float
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const float2 p0 = Elem<E>::unpack2(g[a].x), p1 = Elem<E>::unpack2(g[a].y);
-    gv[a][0] = p0.x, gv[a][1] = p0.y, gv[a][2] = p1.x, gv[a][3] = p1.y;
+    const float ctr = a < 3 ? kGateCenter : 0.f;  // sigmoid gates are stored centred
+    gv[a][0] = p0.x + ctr, gv[a][1] = p0.y + ctr, gv[a][2] = p1.x + ctr, gv[a][3] = p1.y + ctr;
   }
   const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
   const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};

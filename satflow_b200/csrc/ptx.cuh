@@ -254,6 +254,12 @@ constexpr float kHScaleInv = 1.f / 4096.f;
 // head-room as dz and need no shift; their small end sits 2-3 bits ABOVE dz's (dz = dh * o(1-o) * ...), and a down-shift
 // only pushes the vanishing gradients of the bottom cells into fp16's subnormals (a 2^-6 shift doubled the error of the
 // 3-layer 5x5 sweep case).  Kept as named constants: a power of two here is exact and free.
+// Saved sigmoid gates i, f, o are stored as (gate - 0.5): around the centre of the sigmoid's range a 16-bit float resolves the
+// DEVIATION from 0.5 with its full mantissa, instead of spending it on the constant part.  With default-initialised
+// weights the gates sit near 0.5 and their rounding was the largest term of the gradient error budget (5.9e-4 of 8.6e-4,
+// tests/probe_error_budget.py); centred storage removes it (oracle emulation: 8.55e-4 -> 6.16e-4, x3 weights 9.96e-4 ->
+// 8.02e-4 = the figures with exact gates).  The tanh gate g is symmetric around 0 already.
+constexpr float kGateCenter = 0.5f;
 // 16-bit cell state (CLSTM_C16): c crosses HBM as c * 2^8.  |c_t| <= t (every step adds |i g| < 1), so 200 steps stay
 // below 65504 / 256; the smallest normal becomes 2.4e-7, which keeps the |c| ~ 1e-5 of a freshly re-initialised network
 // (CloudGAN, see kHScale) at full 11-bit precision.

@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) rollout_persist_kernel(const 
         }
         if (p.training) {
 #pragma unroll
+          for (int e = 0; e < 16; ++e) gi[e] -= kGateCenter, gf[e] -= kGateCenter, go[e] -= kGateCenter;  // stored centred
+#pragma unroll
           for (uint32_t j = 0; j < 2; ++j) {
             *reinterpret_cast<uint4*>(stg + kStgG + 0 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gi + 8 * j);
             *reinterpret_cast<uint4*>(stg + kStgG + 1 * 4096 + r * 32 + ((j ^ x32) << 4)) = pack8(gf + 8 * j);
