@@ -65,7 +65,7 @@ def ncu_traffic(kernel_substr: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, read from the committed
     `ncu --set full` summary (tools/ncu_summary.py output under profiles/); (None, None) if no capture is committed."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for name in ("r2h_ncu_full_summary.csv", "r2e_ncu_full_summary.csv", "r2_ncu_full_summary.csv", "r1_v2_ncu_full_summary.csv"):
+    for name in ("r2k_ncu_full_summary.csv", "r2h_ncu_full_summary.csv", "r2e_ncu_full_summary.csv", "r2_ncu_full_summary.csv", "r1_v2_ncu_full_summary.csv"):
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.isfile(path):
             continue
