@@ -527,7 +527,7 @@ void carve_cell(Carver& sv, Carver& sc, CellState& cs, const Ctx& ctx) {
   cs.wp = sv.take<void>(static_cast<size_t>(4 * HP) * cs.Kf * 2);
   cs.bias_p = sv.take<float>(static_cast<size_t>(4 * HP) * 4);
   cs.h = sv.take<void>(static_cast<size_t>(cs.slots_h) * npix * HP * 2);
-  cs.c = sv.take<float>(static_cast<size_t>(cs.slots_c) * npix * HP * 4);
+  cs.c = sv.take<float>(static_cast<size_t>(cs.slots_c) * npix * HP * (ctx.c16 ? 2 : 4));  // 16-bit stacks: half the bytes
   if (ctx.training) {
     cs.wd = sv.take<void>(static_cast<size_t>(cs.rows_d) * cs.Kd * 2);
     cs.gates = sv.take<void>(static_cast<size_t>(cs.T) * npix * 4 * HP * 2);
@@ -961,8 +961,8 @@ int cell_dgrad(const Ctx& ctx, CellState& cs, cudaStream_t st, int buf = 0) {
 // slot of a cell's h / c state after `s` steps (s = 0: initial zeros)
 inline int hslot(const CellState& cs, int s) { return s % cs.slots_h; }
 inline int cslot(const CellState& cs, int s) { return s % cs.slots_c; }
-// Address of slot `slot` of a cell's c stack: fp32 [npix][HP], or E [npix][HP] times kCScale when ctx.c16 (the stack keeps
-// its fp32-sized allocation; the typed pointer is only a handle for the kernels, which know the format).
+// Address of slot `slot` of a cell's c stack: fp32 [npix][HP], or E [npix][HP] times kCScale when ctx.c16 (the float-typed
+// pointer is only a handle for the kernels, which know the format).
 inline float* cptr(const Ctx& ctx, const CellState& cs, int slot) {
   const size_t slot_floats = ctx.geo.npix() * ctx.HP / (ctx.c16 ? 2 : 1);
   return cs.c + static_cast<size_t>(slot) * slot_floats;
@@ -2111,7 +2111,7 @@ int clstm_plan_bind(clstm_plan_t* p, void* workspace, size_t bytes, void* stream
     CellState& cs = p->cells[k];
     CU_TRY(cudaMemsetAsync(static_cast<uint8_t*>(cs.h) + static_cast<size_t>(hslot(cs, 0)) * npix * ctx.HP * 2, 0,
                            npix * ctx.HP * 2, st));
-    CU_TRY(cudaMemsetAsync(cs.c, 0, npix * ctx.HP * 4, st));
+    CU_TRY(cudaMemsetAsync(cs.c, 0, npix * ctx.HP * (ctx.c16 ? 2 : 4), st));
     RC_TRY(map_cell(cs, ctx));
   }
   const long long ximgs = static_cast<long long>(c.t_in) * c.batch;
