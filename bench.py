@@ -215,7 +215,7 @@ def workload_config(n, global_batch=None):
                      f"{CFG['hw']}x{CFG['hw']}, {CFG['t_in']} in / {CFG['t_out']} out, batch {per}/GPU, "
                      "fwd+bwd+grad-allreduce+Adam (BASELINE configs[2]; shape of configs[1])"),
         "global_batch": per * n, "parallelism": f"dp{n}",
-        "l2": "working set (71 GB of saved states per step) >> 126 MB L2; no flush needed",
+        "l2": "working set (67 GB workspace of saved states, ~335 GB of HBM traffic per step) >> 126 MB L2; no flush needed",
     }
     if global_batch:
         d["global_batch"] = global_batch
