@@ -71,6 +71,33 @@ def test_workspace_scales_with_saved_states():
     assert sizes[1] - sizes[0] < 2 * per_step + 64 * 1024
 
 
+def test_large_fp16_plans_keep_the_cell_state_in_16_bits(monkeypatch):
+    """CLSTM_C16 (DESIGN.md finding 19) is decided when the plan is created: fp16 rollouts with more tiles than SMs and
+    at most 200 steps halve their c stacks; small plans (persistent chain), bf16 plans and long rollouts keep fp32."""
+    L = _lib.lib()
+
+    def ws(**kw):
+        cfg = _lib.Config(kw.get("batch", 16), 256, 256, 12, 64, 12, 2, 3, 3, kw.get("t_in", 12), kw.get("t_out", 24),
+                          kw.get("dtype", _lib.CLSTM_F16), 1, 0.0)
+        h = ctypes.c_void_p()
+        assert L.clstm_plan_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+        n = L.clstm_plan_workspace_bytes(h)
+        L.clstm_plan_destroy(h)
+        return n
+
+    npix, HP = 16 * 256 * 256, 64
+    c_fp32 = (2 * 13 + 2 * 25) * npix * HP * 4  # 2 encoder + 2 decoder cells, T + 1 slots each
+    monkeypatch.setenv("CLSTM_C16", "0")
+    base = ws()
+    monkeypatch.setenv("CLSTM_C16", "1")
+    assert abs((base - ws()) - c_fp32 // 2) < (1 << 20)
+    monkeypatch.setenv("CLSTM_C16", "0")
+    base_bf16, base_long = ws(dtype=_lib.CLSTM_BF16), ws(batch=1, t_out=201)
+    monkeypatch.setenv("CLSTM_C16", "1")
+    assert ws(dtype=_lib.CLSTM_BF16) == base_bf16
+    assert ws(batch=1, t_out=201) == base_long
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     assert _lib.lib().clstm_device_check(0) == -3
